@@ -1,0 +1,106 @@
+/* xmm_b200.h -- C ABI of libxmm_b200.so: the B200 (sm_100a) kernels behind the RRDB hot
+ * path of SamSweere/xmm-superres-denoise.
+ *
+ * The reference is pure Python; it has no FFI of its own.  Each entry point below names
+ * the reference code (path:line under xmm_superres_denoise/) whose arithmetic it
+ * replaces.  The Python host layer (xmm_superres_denoise_b200/) binds these with ctypes
+ * and keeps the reference's class/function names; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless a name ends in _host.  Buffers are owned
+ *     by the caller and only borrowed for the duration of the call; the library keeps no
+ *     pointer except cached TMA descriptors keyed by (pointer, shape).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Every call is asynchronous with respect to the host.
+ *   - Return value: 0 on success, otherwise an XMM_ERR_* code; xmm_last_error() returns a
+ *     thread-local human-readable message.  There is no CPU fallback anywhere.
+ *   - Activations are NHWC bf16 "channel-window" tensors: a base pointer, the number of
+ *     channels per pixel of the underlying buffer (ctot) and the first channel (coff).
+ *     This is how the dense-block torch.cat (rrdb_blocks.py:49-52) disappears.
+ */
+#ifndef XMM_B200_H_
+#define XMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XMM_OK 0
+#define XMM_ERR_INVALID_ARGUMENT 1
+#define XMM_ERR_UNSUPPORTED_DEVICE 2
+#define XMM_ERR_CUDA 3
+#define XMM_ERR_UNSUPPORTED_SHAPE 4
+
+/* Library / device ------------------------------------------------------------------ */
+const char* xmm_last_error(void);
+int xmm_version(void);
+/* 0 iff the current device is compute capability 10.x (sm_100a image present). */
+int xmm_check_device(void);
+
+/* Weight repacking ------------------------------------------------------------------- */
+/* One source tensor contributing a run of K (input-channel) positions of a packed layer.
+ * src is an nn.Conv2d weight, fp32 OIHW [O][src_cin][3][3].
+ *   transpose == 0 (forward):  packed row n = O index o_off+n, packed k = I index i_off+c
+ *   transpose == 1 (data grad): packed row n = I index i_off+n, packed k = O index o_off+c,
+ *                               taps flipped (dL/dx of a correlation is a convolution)   */
+typedef struct {
+  const float* src;
+  int src_cin;
+  int o_off, i_off;
+  int transpose;
+  int k_off, k_count;
+  float scale;
+} xmm_pack_segment;
+
+typedef struct {
+  void* dst;          /* blob: nchunks*9*nt*kc bf16 (swizzled) then nt fp32 biases        */
+  const float* bias;  /* fp32 [O] or NULL; only used when seg[0].transpose == 0           */
+  int nt;             /* rows (output channels of the packed GEMM), multiple of 32        */
+  int kc;             /* K chunk: 32 or 64 channels                                        */
+  int nchunks;        /* K / kc                                                            */
+  int nseg;           /* 1..5                                                              */
+  int perm;           /* 1: PixelShuffle(2) channel permutation on the O index             */
+  int n_valid;        /* rows >= n_valid are zero                                          */
+  xmm_pack_segment seg[5];
+} xmm_pack_job;
+
+/* Bytes of one packed blob. */
+size_t xmm_pack_blob_bytes(int nt, int kc, int nchunks);
+/* jobs_dev: device array of njobs jobs.  Replaces nothing in the reference -- it is the
+ * OIHW fp32 -> tensor-core image conversion run after every optimizer step.              */
+int xmm_pack_weights(const xmm_pack_job* jobs_dev, int njobs, void* stream);
+
+/* 3x3 convolution on tensor cores ---------------------------------------------------- */
+/* Replaces nn.Conv2d(k=3,s=1,p=1) + torch.cat + LeakyReLU + residual arithmetic of
+ * rrdb_blocks.py:37-54,66-70 and generator_rrdb.py:66-69,93-107; with `mask` it is also
+ * the data-gradient of the same layers (autograd's conv backward + LeakyReLU backward).
+ *   v      = acc + bias
+ *   v      = v > 0 ? v : lrelu_slope * v
+ *   v     *= (mask[p][n] > 0 ? 1 : mask_slope)           if mask
+ *   out    = s0*v + s1*r1[p][n] + s2*r2[p][n]                                            */
+typedef struct {
+  const void* in;     /* bf16 NHWC [batch][height][width][in_ctot]                         */
+  int in_ctot, in_coff, cin; /* cin multiple of kc                                         */
+  const void* wblob;  /* from xmm_pack_weights, nt == cout                                 */
+  int kc;
+  int cout;           /* 32, 64, 128 or 256                                                */
+  int batch, height, width;
+  float lrelu_slope;  /* 1.0f = no activation                                              */
+  const void* mask; int mask_ctot, mask_coff; float mask_slope;
+  float s0;
+  const void* r1; int r1_ctot, r1_coff; float s1;
+  const void* r2; int r2_ctot, r2_coff; float s2;
+  void* out; int out_ctot, out_coff;
+  int pixel_shuffle;  /* 1: out is [batch][2*height][2*width][out_ctot], cout/4 channels   */
+  int tap_mode;       /* 0 = library default; 1..3 force a shared-memory tap layout (probe only) */
+} xmm_conv3x3_params;
+
+int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMM_B200_H_ */

@@ -1,0 +1,333 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces the nn.Conv2d calls of the reference's dense blocks
+// (xmm_superres_denoise/models/modules/rrdb_blocks.py:27-31,49-52 and
+// generator_rrdb.py:39-45,93-101) *and* the torch.cat that feeds them: the input is a
+// channel window [coff, coff+cin) of one NHWC bf16 buffer, the output a channel window of
+// another (or the same) buffer, so the dense connection is pointer arithmetic.
+//
+// GEMM mapping (per CTA tile): M = 128 output pixels (16 rows x 8 cols), N = Cout,
+// K = 9 taps x Cin.  One TMA box per K-chunk brings the (16+2)x(8+2) haloed pixel patch
+// x KC channels into shared memory once; the 9 taps are 9 *views* of that patch (UMMA
+// descriptor start address + stride), so activations cross L2->SMEM 1.4x, not 9x.
+// Weights for the whole layer stay resident in shared memory for the life of the
+// persistent CTA.  Accumulators live in TMEM (double buffered) and the epilogue warps
+// apply bias / LeakyReLU / mask / scaled residuals and store bf16 while the next tile's
+// MMAs run.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx_sm100.cuh"
+
+namespace xmm {
+
+constexpr int kTileH = 16;
+constexpr int kTileW = 8;
+constexpr int kHaloH = kTileH + 2;
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 192;
+
+// How the 9 tap views are formed from shared memory (probe-selectable):
+//   kTapHalo : one haloed [18][10] patch; tap = start-address offset, SBO = 10 rows.
+//   kTapHaloBaseOff : same, plus the descriptor's base_offset field = (start>>7)&7.
+//   kTapDx3  : three dx-shifted dense [18][8] patches; tap dy = 8-row aligned offset.
+enum TapMode : int { kTapHalo = 0, kTapHaloBaseOff = 1, kTapDx3 = 2 };
+
+struct ConvEpilogue {
+  // v = acc + bias[n];  v = v > 0 ? v : lrelu_slope * v;
+  // v *= (mask[p][n] > 0 ? 1 : mask_slope)            (mask == nullptr: skipped)
+  // out[p][n] = s0 * v + s1 * r1[p][n] + s2 * r2[p][n] (r == nullptr: term skipped)
+  float lrelu_slope;
+  float mask_slope;
+  float s0, s1, s2;
+  const __nv_bfloat16* mask;
+  int mask_ctot, mask_coff;
+  const __nv_bfloat16* r1;
+  int r1_ctot, r1_coff;
+  const __nv_bfloat16* r2;
+  int r2_ctot, r2_coff;
+  __nv_bfloat16* out;
+  int out_ctot, out_coff;
+  int pixel_shuffle;  // 1: out is [B][2H][2W][out_ctot]; column group g=(i,j) -> pixel (2y+i,2x+j)
+};
+
+struct ConvArgs {
+  const void* wblob;  // packed weights image + bias (see pack_weights.cuh)
+  uint32_t w_bytes;   // bytes of the weight image (multiple of 1024)
+  int nchunks;        // Cin / KC
+  int cin_off;        // first input channel inside the input buffer
+  int batch, height, width;
+  int tiles_x, tiles_y, num_tiles;
+  int stages;
+  ConvEpilogue epi;
+};
+
+template <int KC, int NT, int MODE>
+struct ConvCfg {
+  static_assert(KC == 32 || KC == 64, "K chunk is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B) channels");
+  static_assert(NT % 32 == 0 && NT >= 32 && NT <= 256, "Cout tile");
+  static constexpr int kRowB = KC * 2;  // bytes of one pixel's K-chunk in shared memory
+  static constexpr uint32_t kLayout = (KC == 64) ? ptx::UMMA_SW128 : ptx::UMMA_SW64;
+  static constexpr int kPitchPx = (MODE == kTapDx3) ? kTileW : kTileW + 2;
+  static constexpr int kSubBytes = kHaloH * kPitchPx * kRowB;
+  static constexpr int kSubStride = (kSubBytes + 1023) / 1024 * 1024;
+  static constexpr int kNumSub = (MODE == kTapDx3) ? 3 : 1;
+  static constexpr int kStageBytes = kNumSub * kSubStride;
+  static constexpr int kStageTx = kNumSub * kSubBytes;
+  static constexpr int kKSteps = KC / 16;
+  static constexpr int kTapBytes = NT * kRowB;  // one (chunk, tap) weight block
+  static constexpr int kTmemCols = (2 * NT <= 32) ? 32 : (2 * NT <= 64) ? 64 : (2 * NT <= 128) ? 128 : (2 * NT <= 256) ? 256 : 512;
+  static constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, NT, 0, 0);
+  static constexpr int kBiasBytes = NT * 4;
+  // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] wbar + tmem ptr
+  static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 16;
+  static size_t smem_bytes(uint32_t w_bytes, int stages) {
+    return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kBarBytes;
+  }
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// Epilogue for 32 accumulator columns [col0, col0+32) of one pixel.
+template <int NT>
+__device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const float* __restrict__ bias_s,
+                                                 uint32_t (&acc)[32], int col0, int b, int y, int x,
+                                                 int H, int W) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float t = __uint_as_float(acc[i]) + bias_s[col0 + i];
+    v[i] = t > 0.f ? t : t * e.lrelu_slope;
+  }
+  const size_t pix = (size_t(b) * H + y) * W + x;
+  if (e.mask != nullptr) {
+    const uint4* mp = reinterpret_cast<const uint4*>(e.mask + pix * e.mask_ctot + e.mask_coff + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float m[8];
+      unpack8(__ldg(mp + q), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[q * 8 + i] *= (m[i] > 0.f ? 1.f : e.mask_slope);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] *= e.s0;
+  if (e.r1 != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(e.r1 + pix * e.r1_ctot + e.r1_coff + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float m[8];
+      unpack8(__ldg(rp + q), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[q * 8 + i] = fmaf(e.s1, m[i], v[q * 8 + i]);
+    }
+  }
+  if (e.r2 != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(e.r2 + pix * e.r2_ctot + e.r2_coff + col0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float m[8];
+      unpack8(__ldg(rp + q), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[q * 8 + i] = fmaf(e.s2, m[i], v[q * 8 + i]);
+    }
+  }
+  uint4* op;
+  if (e.pixel_shuffle) {
+    constexpr int kGroup = NT / 4;  // channels of the shuffled (HR) tensor
+    const int g = col0 / kGroup, c = col0 % kGroup;
+    const size_t hp = (size_t(b) * (2 * H) + (2 * y + (g >> 1))) * (2 * W) + (2 * x + (g & 1));
+    op = reinterpret_cast<uint4*>(e.out + hp * e.out_ctot + e.out_coff + c);
+  } else {
+    op = reinterpret_cast<uint4*>(e.out + pix * e.out_ctot + e.out_coff + col0);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) op[q] = pack8(v + q * 8);
+}
+
+template <int KC, int NT, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs args) {
+  using Cfg = ConvCfg<KC, NT, MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;                                                   // weights image
+  float* bias_s = reinterpret_cast<float*>(smem + args.w_bytes);         // NT floats (same bulk copy)
+  uint8_t* stage_s = smem + ((args.w_bytes + Cfg::kBiasBytes + 1023) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + size_t(args.stages) * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_in);
+    for (int s = 0; s < args.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 4);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int tiles_per_img = args.tiles_x * args.tiles_y;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t wtot = args.w_bytes + Cfg::kBiasBytes;
+      ptx::mbar_expect_tx(w_bar, wtot);
+      const uint8_t* gsrc = static_cast<const uint8_t*>(args.wblob);
+      for (uint32_t off = 0; off < wtot; off += 32768u) {
+        const uint32_t n = (wtot - off < 32768u) ? (wtot - off) : 32768u;
+        ptx::bulk_load(w_s + off, gsrc + off, n, w_bar);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int ty = r / args.tiles_x;
+        const int tx = r - ty * args.tiles_x;
+        const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
+        for (int ch = 0; ch < args.nchunks; ++ch) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageTx);
+          uint8_t* dst = stage_s + size_t(stage) * Cfg::kStageBytes;
+          const int c0 = args.cin_off + ch * KC;
+#pragma unroll
+          for (int sub = 0; sub < Cfg::kNumSub; ++sub)
+            ptx::tma_load_4d(dst + sub * Cfg::kSubStride, &tmap_in, &full_bar[stage], c0, x0 + sub, y0, b);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      ptx::mbar_wait(w_bar, 0);
+      ptx::tc_fence_after();
+      const uint32_t w_addr = ptx::smem_u32(w_s);
+      const uint32_t st_addr = ptx::smem_u32(stage_s);
+      const uint64_t bdesc0 = ptx::umma_smem_desc(w_addr, 16, 8 * Cfg::kRowB, Cfg::kLayout);
+      const uint64_t adesc0 = ptx::umma_smem_desc(0, 16, Cfg::kPitchPx * Cfg::kRowB, Cfg::kLayout);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_addr = tmem_base + uint32_t(acc * NT);
+        for (int ch = 0; ch < args.nchunks; ++ch) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_stage = st_addr + uint32_t(stage) * Cfg::kStageBytes;
+          const uint64_t bdesc_ch = bdesc0 + uint64_t((uint32_t(ch) * 9u * Cfg::kTapBytes) >> 4);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+            uint32_t a_off;
+            if (MODE == kTapDx3)
+              a_off = uint32_t(dx * Cfg::kSubStride + dy * kTileW * Cfg::kRowB);
+            else
+              a_off = uint32_t((dy * Cfg::kPitchPx + dx) * Cfg::kRowB);
+#pragma unroll
+            for (int ks = 0; ks < Cfg::kKSteps; ++ks) {
+              const uint32_t a_addr = a_stage + a_off + uint32_t(ks * 32);
+              uint64_t adesc = adesc0 | uint64_t((a_addr & 0x3FFFFu) >> 4);
+              if (MODE == kTapHaloBaseOff) adesc |= uint64_t((a_addr >> 7) & 7u) << 49;
+              const uint64_t bdesc = bdesc_ch + uint64_t((uint32_t(tap) * Cfg::kTapBytes + uint32_t(ks * 32)) >> 4);
+              ptx::umma_ss(d_addr, adesc, bdesc, Cfg::kIdesc, (ch | tap | ks) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int py = m >> 3, px = m & 7;
+    ptx::mbar_wait(w_bar, 0);  // bias rides with the weights
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int ty = r / args.tiles_x;
+      const int tx = r - ty * args.tiles_x;
+      const int y = ty * kTileH + py, x = tx * kTileW + px;
+      const bool valid = (y < args.height) && (x < args.width);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * NT);
+#pragma unroll 1
+      for (int cc = 0; cc < NT / 32; ++cc) {
+        uint32_t accr[32];
+        ptx::tmem_ld_32x32(t_addr + uint32_t(cc * 32), accr);
+        ptx::tmem_ld_wait();
+        if (cc == NT / 32 - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+        if (valid) conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace xmm

@@ -1,0 +1,173 @@
+// libxmm_b200.so -- C ABI launchers (see include/xmm_b200.h for the contract).
+#include "../../include/xmm_b200.h"
+
+#include <unordered_map>
+
+#include "conv3x3_tc.cuh"
+#include "host_common.cuh"
+#include "pack_weights.cuh"
+
+#ifndef XMM_DEFAULT_TAP_MODE
+#define XMM_DEFAULT_TAP_MODE 0
+#endif
+
+using namespace xmm;
+
+extern "C" const char* xmm_last_error(void) { return last_error_ref().c_str(); }
+extern "C" int xmm_version(void) { return 100; }
+extern "C" int xmm_check_device(void) {
+  DeviceInfo d;
+  return require_sm100(&d);
+}
+
+// ----------------------------------------------------------------------------- packing
+extern "C" size_t xmm_pack_blob_bytes(int nt, int kc, int nchunks) {
+  return size_t(nchunks) * 9 * nt * kc * 2 + size_t(nt) * 4;
+}
+
+extern "C" int xmm_pack_weights(const xmm_pack_job* jobs_dev, int njobs, void* stream) {
+  DeviceInfo d;
+  int rc = require_sm100(&d);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(jobs_dev != nullptr && njobs > 0, "xmm_pack_weights: empty job table");
+  dim3 grid(45, njobs);
+  pack_jobs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+// ----------------------------------------------------------------------------- conv3x3
+namespace {
+
+struct TmapKey {
+  const void* base;
+  int batch, height, width, ctot, box_c, box_w, box_h;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && batch == o.batch && height == o.height && width == o.width && ctot == o.ctot &&
+           box_c == o.box_c && box_w == o.box_w && box_h == o.box_h;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.batch); mix(k.height); mix(k.width); mix(k.ctot); mix(k.box_c); mix(k.box_w); mix(k.box_h);
+    return h;
+  }
+};
+
+// Descriptors are pure functions of (pointer, shape); caching only saves the encode call.
+int cached_tmap(CUtensorMap* out, const void* base, int batch, int height, int width, int ctot, int box_c,
+                int box_w, int box_h) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{base, batch, height, width, ctot, box_c, box_w, box_h};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return XMM_OK;
+  }
+  int rc = make_nhwc_tmap(out, base, batch, height, width, ctot, box_c, box_w, box_h, false);
+  if (rc != XMM_OK) return rc;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return XMM_OK;
+}
+
+template <int KC, int NT, int MODE>
+int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  using Cfg = ConvCfg<KC, NT, MODE>;
+  ConvArgs a{};
+  a.wblob = p.wblob;
+  a.nchunks = p.cin / KC;
+  a.w_bytes = uint32_t(a.nchunks) * 9u * Cfg::kTapBytes;
+  a.cin_off = p.in_coff;
+  a.batch = p.batch;
+  a.height = p.height;
+  a.width = p.width;
+  a.tiles_x = (p.width + kTileW - 1) / kTileW;
+  a.tiles_y = (p.height + kTileH - 1) / kTileH;
+  a.num_tiles = a.tiles_x * a.tiles_y * p.batch;
+  const size_t fixed = Cfg::smem_bytes(a.w_bytes, 0);
+  if (fixed + 2 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin))
+    return fail(XMM_ERR_UNSUPPORTED_SHAPE,
+                "conv3x3: weights of cin=%d cout=%d (%u B) do not fit in shared memory next to 2 pipeline stages",
+                p.cin, p.cout, a.w_bytes);
+  int stages = int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  a.stages = stages;
+  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages);
+
+  ConvEpilogue& e = a.epi;
+  e.lrelu_slope = p.lrelu_slope;
+  e.mask_slope = p.mask_slope;
+  e.s0 = p.s0; e.s1 = p.s1; e.s2 = p.s2;
+  e.mask = static_cast<const __nv_bfloat16*>(p.mask); e.mask_ctot = p.mask_ctot; e.mask_coff = p.mask_coff;
+  e.r1 = static_cast<const __nv_bfloat16*>(p.r1); e.r1_ctot = p.r1_ctot; e.r1_coff = p.r1_coff;
+  e.r2 = static_cast<const __nv_bfloat16*>(p.r2); e.r2_ctot = p.r2_ctot; e.r2_coff = p.r2_coff;
+  e.out = static_cast<__nv_bfloat16*>(p.out); e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
+  e.pixel_shuffle = p.pixel_shuffle;
+
+  CUtensorMap tmap;
+  int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, Cfg::kPitchPx, kHaloH);
+  if (rc != XMM_OK) return rc;
+
+  static bool attr_set = false;  // per instantiation; benign race (idempotent call)
+  if (!attr_set) {
+    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dev.max_smem_optin));
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
+  conv3x3_tc_kernel<KC, NT, MODE><<<grid, kConvThreads, smem, stream>>>(tmap, a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+template <int KC, int NT>
+int launch_conv_mode(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  const int mode = p.tap_mode <= 0 ? XMM_DEFAULT_TAP_MODE : p.tap_mode - 1;
+  switch (mode) {
+    case kTapHalo: return launch_conv<KC, NT, kTapHalo>(p, dev, stream);
+    case kTapHaloBaseOff: return launch_conv<KC, NT, kTapHaloBaseOff>(p, dev, stream);
+    case kTapDx3: return launch_conv<KC, NT, kTapDx3>(p, dev, stream);
+    default: return fail(XMM_ERR_INVALID_ARGUMENT, "conv3x3: unknown tap_mode %d", mode);
+  }
+}
+
+}  // namespace
+
+extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "conv3x3: null params");
+  const xmm_conv3x3_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.in && p.out && p.wblob, "conv3x3: null tensor pointer");
+  XMM_REQUIRE(p.batch > 0 && p.height > 0 && p.width > 0, "conv3x3: bad shape %dx%dx%d", p.batch, p.height, p.width);
+  XMM_REQUIRE(p.kc == 32 || p.kc == 64, "conv3x3: kc must be 32 or 64 (got %d)", p.kc);
+  XMM_REQUIRE(p.cin > 0 && p.cin % p.kc == 0, "conv3x3: cin=%d is not a multiple of kc=%d", p.cin, p.kc);
+  XMM_REQUIRE(p.in_ctot % 8 == 0 && p.in_coff % 8 == 0 && p.in_coff + p.cin <= p.in_ctot,
+              "conv3x3: input channel window [%d,%d) of %d", p.in_coff, p.in_coff + p.cin, p.in_ctot);
+  const int out_c = p.pixel_shuffle ? p.cout / 4 : p.cout;
+  XMM_REQUIRE(p.out_ctot % 8 == 0 && p.out_coff % 8 == 0 && p.out_coff + out_c <= p.out_ctot,
+              "conv3x3: output channel window [%d,%d) of %d", p.out_coff, p.out_coff + out_c, p.out_ctot);
+  XMM_REQUIRE(!p.mask || (p.mask_ctot % 8 == 0 && p.mask_coff % 8 == 0), "conv3x3: mask window alignment");
+  XMM_REQUIRE(!p.r1 || (p.r1_ctot % 8 == 0 && p.r1_coff % 8 == 0), "conv3x3: r1 window alignment");
+  XMM_REQUIRE(!p.r2 || (p.r2_ctot % 8 == 0 && p.r2_coff % 8 == 0), "conv3x3: r2 window alignment");
+  XMM_REQUIRE(!p.pixel_shuffle || (!p.mask && !p.r1 && !p.r2 && p.cout % 128 == 0),
+              "conv3x3: pixel_shuffle needs cout %% 128 == 0 and no mask/residual");
+  XMM_REQUIRE((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p.wblob) & 15) == 0,
+              "conv3x3: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define XMM_CONV_CASE(KC_, NT_) \
+  if (p.kc == KC_ && p.cout == NT_) return launch_conv_mode<KC_, NT_>(p, dev, s);
+  XMM_CONV_CASE(32, 32)
+  XMM_CONV_CASE(32, 128)
+  XMM_CONV_CASE(64, 64)
+  XMM_CONV_CASE(64, 256)
+#undef XMM_CONV_CASE
+  return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3: no kernel for kc=%d cout=%d", p.kc, p.cout);
+}
