@@ -100,6 +100,66 @@ typedef struct {
 
 int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);
 
+/* Input transforms ------------------------------------------------------------------- */
+#define XMM_STRETCH_LINEAR 0
+#define XMM_STRETCH_SQRT 1
+#define XMM_STRETCH_ASINH 2
+#define XMM_STRETCH_LOG 3
+
+/* Replaces Normalize.normalize_image (transforms/normalize.py:66-82) fused with the detector
+ * mask multiply (data/dataset.py:41-42) and the counts -> rate division the refactor lost
+ * (SURVEY I4): v = in * pre_scale * mask; v = clamp(v, 0, max_val) / max_val; stretch;
+ * clamp(0,1).  max_val <= 0 selects the reference's "divide by the image maximum" branch
+ * (fp32 input only; `scratch` = one device float).                                        */
+typedef struct {
+  const void* in;       /* fp32 or int32, n elements                                       */
+  int in_is_int32;
+  const uint8_t* mask;  /* optional, mask_n elements, repeated every mask_n                */
+  size_t mask_n;
+  float* out;           /* fp32, n elements (may alias `in` when in is fp32)               */
+  size_t n;
+  float pre_scale;
+  float max_val;
+  int stretch_mode;
+  float* scratch;
+} xmm_normalize_params;
+int xmm_normalize(const xmm_normalize_params* p, void* stream);
+
+/* Replaces Normalize.denormalize_image (transforms/normalize.py:84-92):
+ * out = clamp(max * denorm(in), 0, max); max_vals_dev holds 1 value or one per image.     */
+int xmm_denormalize(const float* in, float* out, size_t n, size_t per_image, const float* max_vals_dev,
+                    int max_n, int stretch_mode, void* stream);
+
+/* Replaces ImageUpsample.__call__ (transforms/imageupsample.py:10-26): nearest upsample by an
+ * integer factor then divide by factor^2.  in [n_img][h][w] fp32 -> out [n_img][h*s][w*s].  */
+int xmm_image_upsample(const float* in, float* out, int n_img, int h, int w, int scale, void* stream);
+
+/* First / last convolution ------------------------------------------------------------ */
+/* conv_first (generator_rrdb.py:31-37,67): fp32 NCHW image -> bf16 NHWC features.          */
+typedef struct {
+  const float* in;    /* [batch][cin][height][width]                                       */
+  const float* weight; /* fp32 OIHW [filters][cin][3][3]                                   */
+  const float* bias;  /* fp32 [filters] or NULL                                            */
+  int batch, cin, height, width, filters;  /* cin 1..4, filters 32 or 64                    */
+  void* out; int out_ctot, out_coff;
+  void* out2; int out2_ctot, out2_coff;    /* optional second copy (trunk skip), or NULL     */
+} xmm_conv_first_params;
+int xmm_conv_first(const xmm_conv_first_params* p, void* stream);
+
+/* conv_last (generator_rrdb.py:48-54,107-108,132-135) + DN input residual + clamp[0,1]
+ * (also covers Model.forward's second clamp, models/model.py:49).                          */
+typedef struct {
+  const void* in; int in_ctot, in_coff;  /* bf16 NHWC, `filters` channels                   */
+  const float* weight; /* fp32 OIHW [cout][filters][3][3]                                  */
+  const float* bias;   /* fp32 [cout] or NULL                                              */
+  const float* residual; /* optional fp32 NCHW [batch][cout][height][width]                */
+  float* out;          /* fp32 NCHW [batch][cout][height][width]                           */
+  float* pre;          /* optional un-clamped copy (training)                              */
+  int batch, cout, height, width, filters;  /* cout 1..4                                    */
+  int clamp;
+} xmm_conv_last_params;
+int xmm_conv_last(const xmm_conv_last_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,19 +102,40 @@ def model_forward(x: Tensor, sd: Mapping[str, Tensor], kind: str, num_upsample: 
     return torch.clamp(y, 0.0, 1.0)
 
 
+def splitmix_uniform(n: int, seed: int) -> "np.ndarray":
+    """n floats in [0,1) from splitmix64(seed, index): closed-form, so fixtures never depend on a
+    library's RNG stream."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        z = np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
 def init_state_dict(kind: str, in_ch: int, out_ch: int, nf: int, nb: int, num_upsample: int = 1,
                     seed: int = 0) -> Dict[str, Tensor]:
-    """Random parameters with the shapes/keys of the reference generators
-    (generator_rrdb.py:10-64,91-101; rrdb_blocks.py:27-31) and nn.Conv2d's default
+    """Deterministic parameters with the keys/shapes of the reference generators
+    (generator_rrdb.py:10-64,91-101; rrdb_blocks.py:27-31), drawn at nn.Conv2d's default
     U(-1/sqrt(fan_in), 1/sqrt(fan_in)) scale; conv_last gets the positive offset of
     generator_rrdb.py:56-64.  The values are NOT the reference's RNG stream."""
-    g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {}
+    counter = [0]
 
-    def conv(name: str, cin: int, cout: int, hi_scale: float = 1.0) -> None:
+    def uniform(shape, lo: float, hi: float) -> Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        counter[0] += 1
+        u = splitmix_uniform(n, seed * 100003 + counter[0])
+        return torch.from_numpy((lo + (hi - lo) * u).astype("float32")).reshape(shape)
+
+    def conv(name: str, cin: int, cout: int) -> None:
         s = 1.0 / math.sqrt(cin * 9)
-        sd[f"{name}.weight"] = (torch.rand(cout, cin, 3, 3, generator=g) * (s * hi_scale + s) - s)
-        sd[f"{name}.bias"] = (torch.rand(cout, generator=g) * (s * hi_scale + s) - s)
+        sd[f"{name}.weight"] = uniform((cout, cin, 3, 3), -s, s)
+        sd[f"{name}.bias"] = uniform((cout,), -s, s)
 
     conv("conv_first", in_ch, nf)
     for i in range(nb):
@@ -123,14 +144,14 @@ def init_state_dict(kind: str, in_ch: int, out_ch: int, nf: int, nb: int, num_up
                 conv(f"rrdb.{i}.RDB{r}.conv{k}", nf * k, nf)
             conv(f"rrdb.{i}.RDB{r}.conv5", nf * 5, nf)
     conv("trunk_conv", nf, nf)
+    # generator_rrdb.py:59-64: stdv = 1/sqrt(weight.size(1)) -- channels only, not fan-in
+    stdv = 1.0 / math.sqrt(nf)
+    sd["conv_last.weight"] = uniform((out_ch, nf, 3, 3), -stdv, 1.01 * stdv)
+    sd["conv_last.bias"] = uniform((out_ch,), -stdv, 1.01 * stdv)
     if kind == "sr":
         for s in range(num_upsample):
             conv(f"upsampling.{3 * s}", nf, nf * 4)
         conv("HRconv", nf, nf)
-    # generator_rrdb.py:59-64: stdv = 1/sqrt(weight.size(1)) -- channels only, not fan-in
-    stdv = 1.0 / math.sqrt(nf)
-    sd["conv_last.weight"] = torch.rand(out_ch, nf, 3, 3, generator=g) * (2.01 * stdv) - stdv
-    sd["conv_last.bias"] = torch.rand(out_ch, generator=g) * (2.01 * stdv) - stdv
     return sd
 
 

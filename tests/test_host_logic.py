@@ -1,0 +1,66 @@
+"""CPU: host-side mirror of the reference interface (names, state_dict, error behaviour)."""
+import pytest
+import torch
+
+from oracle import ref_loader
+from oracle import rrdb_oracle as O
+from xmm_superres_denoise_b200.models import GeneratorRRDB_DN, GeneratorRRDB_SR
+from xmm_superres_denoise_b200.models.modules import RRDB, ResidualDenseBlock_5C, make_layer
+from xmm_superres_denoise_b200.transforms import ImageUpsample, Normalize
+
+
+@pytest.mark.parametrize("kind", ["dn", "sr"])
+def test_state_dict_keys_shapes_and_param_count(kind):
+    m = GeneratorRRDB_DN(1, 1, 32, 4) if kind == "dn" else GeneratorRRDB_SR(1, 1, 32, 4, num_upsample=1)
+    sd = m.state_dict()
+    want = O.init_state_dict(kind, 1, 1, 32, 4, 1)
+    assert sorted(sd.keys()) == sorted(want.keys())
+    assert all(tuple(sd[k].shape) == tuple(want[k].shape) for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == (1670657 if kind == "dn" else 1716897)
+    assert len(sd) == (126 if kind == "dn" else 130)
+    m.load_state_dict(want)  # strict
+
+
+def test_default_num_upsample_and_attributes():
+    m = GeneratorRRDB_SR(1, 1, 32, 1)
+    assert m.num_upsample == 2 and "upsampling.3.weight" in m.state_dict()
+    assert (m.in_channels, m.out_channels, m.num_filters, m.num_res_blocks, m.memory_efficient) == (1, 1, 32, 1, False)
+    assert isinstance(m.rrdb[0], RRDB) and isinstance(m.rrdb[0].RDB2, ResidualDenseBlock_5C)
+    assert len(make_layer(lambda: RRDB(32, 32), 3)) == 3
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+@pytest.mark.parametrize("kind", ["dn", "sr"])
+def test_same_seed_gives_the_reference_initialisation(kind):
+    ref = ref_loader.load_reference()
+    torch.manual_seed(123)
+    a = ref.GeneratorRRDB_DN(1, 1, 32, 2) if kind == "dn" else ref.GeneratorRRDB_SR(1, 1, 32, 2, num_upsample=1)
+    torch.manual_seed(123)
+    b = GeneratorRRDB_DN(1, 1, 32, 2) if kind == "dn" else GeneratorRRDB_SR(1, 1, 32, 2, num_upsample=1)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+def test_no_cpu_fallback():
+    m = GeneratorRRDB_DN(1, 1, 32, 1).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.rand(1, 1, 16, 16))
+    with pytest.raises(RuntimeError):
+        Normalize(1.0, 1.0, "sqrt").normalize_lr_image(torch.rand(4, 4))
+    with pytest.raises(RuntimeError):
+        ImageUpsample(2)(torch.rand(1, 1, 4, 4))
+    with pytest.raises(NotImplementedError):
+        GeneratorRRDB_DN(1, 1, 48, 1).eval()._get_engine()
+
+
+def test_normalize_interface():
+    n = Normalize(lr_max=0.0022336, hr_max=0.0005584, stretch_mode="asinh")
+    assert n.stretch_mode == "asinh" and n.lr_max.ndim == 0 and abs(float(n.hr_max) - 0.0005584) < 1e-9
+    assert n.normalize_hr_image(None) is None
+    x = torch.linspace(0, 1, 9)
+    assert torch.allclose(n.denorm(n.norm(x)), x, atol=1e-6)
+    with pytest.raises(ValueError, match="is not implemented"):
+        Normalize(1.0, 1.0, "cbrt")
+    with pytest.raises(ValueError):
+        ImageUpsample(1.5)

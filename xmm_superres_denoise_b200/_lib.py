@@ -1,0 +1,118 @@
+"""ctypes binding of ``libxmm_b200.so`` (the C ABI declared in ``include/xmm_b200.h``).
+
+The product path has no CPU or PyTorch-eager fallback: if the shared library is missing, or
+the device is not an sm_100a GPU, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxmm_b200.so")
+
+
+class PackSegment(Structure):
+    _fields_ = [("src", c_void_p), ("src_cin", c_int), ("o_off", c_int), ("i_off", c_int), ("transpose", c_int),
+                ("k_off", c_int), ("k_count", c_int), ("scale", c_float)]
+
+
+class PackJob(Structure):
+    _fields_ = [("dst", c_void_p), ("bias", c_void_p), ("nt", c_int), ("kc", c_int), ("nchunks", c_int),
+                ("nseg", c_int), ("perm", c_int), ("n_valid", c_int), ("seg", PackSegment * 5)]
+
+
+class Conv3x3Params(Structure):
+    _fields_ = [("in_", c_void_p), ("in_ctot", c_int), ("in_coff", c_int), ("cin", c_int),
+                ("wblob", c_void_p), ("kc", c_int), ("cout", c_int),
+                ("batch", c_int), ("height", c_int), ("width", c_int),
+                ("lrelu_slope", c_float),
+                ("mask", c_void_p), ("mask_ctot", c_int), ("mask_coff", c_int), ("mask_slope", c_float),
+                ("s0", c_float),
+                ("r1", c_void_p), ("r1_ctot", c_int), ("r1_coff", c_int), ("s1", c_float),
+                ("r2", c_void_p), ("r2_ctot", c_int), ("r2_coff", c_int), ("s2", c_float),
+                ("out", c_void_p), ("out_ctot", c_int), ("out_coff", c_int),
+                ("pixel_shuffle", c_int), ("tap_mode", c_int)]
+
+
+class NormalizeParams(Structure):
+    _fields_ = [("in_", c_void_p), ("in_is_int32", c_int), ("mask", c_void_p), ("mask_n", c_size_t),
+                ("out", c_void_p), ("n", c_size_t), ("pre_scale", c_float), ("max_val", c_float),
+                ("stretch_mode", c_int), ("scratch", c_void_p)]
+
+
+class ConvFirstParams(Structure):
+    _fields_ = [("in_", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
+                ("batch", c_int), ("cin", c_int), ("height", c_int), ("width", c_int), ("filters", c_int),
+                ("out", c_void_p), ("out_ctot", c_int), ("out_coff", c_int),
+                ("out2", c_void_p), ("out2_ctot", c_int), ("out2_coff", c_int)]
+
+
+class ConvLastParams(Structure):
+    _fields_ = [("in_", c_void_p), ("in_ctot", c_int), ("in_coff", c_int),
+                ("weight", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
+                ("out", c_void_p), ("pre", c_void_p),
+                ("batch", c_int), ("cout", c_int), ("height", c_int), ("width", c_int), ("filters", c_int),
+                ("clamp", c_int)]
+
+
+# name -> (restype, argtypes); the non-GPU test-suite checks every name in include/xmm_b200.h is here
+# and exported by the shared object.
+SIGNATURES = {
+    "xmm_last_error": (c_char_p, []),
+    "xmm_version": (c_int, []),
+    "xmm_check_device": (c_int, []),
+    "xmm_pack_blob_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "xmm_pack_weights": (c_int, [c_void_p, c_int, c_void_p]),
+    "xmm_conv3x3_bf16": (c_int, [POINTER(Conv3x3Params), c_void_p]),
+    "xmm_normalize": (c_int, [POINTER(NormalizeParams), c_void_p]),
+    "xmm_denormalize": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_int, c_void_p]),
+    "xmm_image_upsample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "xmm_conv_first": (c_int, [POINTER(ConvFirstParams), c_void_p]),
+    "xmm_conv_last": (c_int, [POINTER(ConvLastParams), c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (no device required)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). xmm_superres_denoise_b200 has no CPU / eager fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().xmm_last_error()
+        raise RuntimeError(f"libxmm_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream (launches join torch's stream order)."""
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda_tensor(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (xmm_superres_denoise_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+
+
+STRETCH_MODES = {"linear": 0, "sqrt": 1, "asinh": 2, "log": 3}

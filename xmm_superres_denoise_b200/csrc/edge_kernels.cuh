@@ -1,0 +1,233 @@
+// HBM-bound kernels at the two ends of the generator:
+//   * normalize / denormalize  (transforms/normalize.py:66-92, data/dataset.py:41-42)
+//   * conv_first  (1..4 -> F channels, generator_rrdb.py:31-37,67): K = 9*Cin is far too small
+//     for an MMA, so it is a CUDA-core stencil that writes the NHWC bf16 feature map;
+//   * conv_last   (F -> 1..4 channels, generator_rrdb.py:48-54,107-108,132-135): a per-pixel
+//     9*F dot product fused with the DN input residual and both clamps (model.py:49).
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "conv3x3_tc.cuh"  // unpack8 / pack8
+
+namespace xmm {
+
+enum StretchMode : int { kLinear = 0, kSqrt = 1, kAsinh = 2, kLog = 3 };
+
+__device__ __forceinline__ float stretch_fwd(float x, int mode) {
+  switch (mode) {
+    case kSqrt: return sqrtf(x);
+    case kAsinh: return asinhf(x / 0.02f) / asinhf(50.0f);   // normalize.py:4-10
+    case kLog: return logf(1000.0f * x + 1.0f) / logf(1000.0f);  // normalize.py:23-26
+    default: return x;
+  }
+}
+__device__ __forceinline__ float stretch_inv(float x, int mode) {
+  switch (mode) {
+    case kSqrt: return x * x;
+    case kAsinh: return 0.02f * sinhf(x * asinhf(50.0f));    // normalize.py:13-19
+    case kLog: return (powf(1000.0f, x) - 1.0f) / 1000.0f;  // normalize.py:29-32
+    default: return x;
+  }
+}
+
+struct NormalizeArgs {
+  const void* in;        // fp32 or int32 [n]
+  const uint8_t* mask;   // optional detector mask, broadcast over the batch: [mask_n]
+  float* out;            // fp32 [n]
+  size_t n;
+  size_t mask_n;         // pixels per image (mask period)
+  int in_is_int32;
+  float pre_scale;       // multiplies the raw value first (1/exposure: counts -> rate)
+  float max_val;         // > 0 ; (the max_val <= 0 branch divides by *dyn_max instead)
+  const float* dyn_max;  // device scalar, used when max_val <= 0
+  int mode;
+};
+
+// 4 elements per thread, 16-byte loads/stores; tail handled by the last threads scalar-wise.
+__global__ void normalize_kernel(const NormalizeArgs a) {
+  const size_t i4 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= a.n) return;
+  const bool clamp_in = a.max_val > 0.0f;
+  const float mx = clamp_in ? a.max_val : *a.dyn_max;
+  float v[4];
+  const int cnt = (a.n - i4 >= 4) ? 4 : int(a.n - i4);
+  if (cnt == 4) {
+    if (a.in_is_int32) {
+      const int4 q = *reinterpret_cast<const int4*>(static_cast<const int*>(a.in) + i4);
+      v[0] = float(q.x); v[1] = float(q.y); v[2] = float(q.z); v[3] = float(q.w);
+    } else {
+      const float4 q = *reinterpret_cast<const float4*>(static_cast<const float*>(a.in) + i4);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+  } else {
+    for (int j = 0; j < cnt; ++j)
+      v[j] = a.in_is_int32 ? float(static_cast<const int*>(a.in)[i4 + j]) : static_cast<const float*>(a.in)[i4 + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < cnt) {
+      float x = v[j] * a.pre_scale;
+      if (a.mask != nullptr) x *= float(a.mask[(i4 + j) % a.mask_n]);
+      // image / max_val is a true division in the reference; keep it a division so results are
+      // bit-identical to torch (x * (1/max) differs in the last ulp).
+      if (clamp_in) x = fminf(fmaxf(x, 0.0f), mx);
+      x = x / mx;
+      x = stretch_fwd(x, a.mode);
+      v[j] = fminf(fmaxf(x, 0.0f), 1.0f);
+    }
+  }
+  if (cnt == 4) {
+    *reinterpret_cast<float4*>(a.out + i4) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    for (int j = 0; j < cnt; ++j) a.out[i4 + j] = v[j];
+  }
+}
+
+// out = clamp(max * denorm(x), 0, max); max_vals has max_n entries (1 = scalar, else one per image)
+__global__ void denormalize_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, size_t per_image,
+                                   const float* __restrict__ max_vals, int max_n, int mode) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float mx = max_vals[max_n == 1 ? 0 : (i / per_image)];
+  float v = mx * stretch_inv(in[i], mode);
+  out[i] = fminf(fmaxf(v, 0.0f), mx);
+}
+
+// max over a float array (normalize's max_val <= 0 branch): atomicMax on the int view is valid for
+// non-negative floats; negative inputs clamp to 0 which matches a counts image.
+__global__ void max_kernel(const float* __restrict__ in, size_t n, float pre_scale, float* __restrict__ out) {
+  float m = 0.0f;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    m = fmaxf(m, in[i] * pre_scale);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+// nearest-neighbour upsample by an integer factor, divided by factor^2 (brightness preserving)
+// -- transforms/imageupsample.py:10-26.  in [n_img][h][w] -> out [n_img][h*s][w*s]
+__global__ void image_upsample_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n_out, int h,
+                                      int w, int s) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int ow = w * s, oh = h * s;
+  const int ox = int(i % ow);
+  const size_t t = i / ow;
+  const int oy = int(t % oh);
+  const size_t img = t / oh;
+  out[i] = in[(img * h + oy / s) * w + ox / s] / float(s * s);
+}
+
+// ------------------------------------------------------------------------------ conv_first
+struct ConvFirstArgs {
+  const float* in;   // fp32 NCHW [B][cin][H][W]
+  const float* w;    // fp32 OIHW [F][cin][3][3]
+  const float* bias; // fp32 [F]
+  __nv_bfloat16* out; int out_ctot, out_coff;
+  __nv_bfloat16* out2; int out2_ctot, out2_coff;  // optional second copy (the trunk skip `fea`)
+  int batch, cin, height, width;
+};
+
+template <int F>
+__global__ void __launch_bounds__(128) conv_first_kernel(const ConvFirstArgs a) {
+  extern __shared__ float wsm[];  // [cin*9][F] + bias[F]
+  const int kw = a.cin * 9;
+  for (int i = threadIdx.x; i < kw * F; i += blockDim.x) {
+    const int f = i % F, k = i / F;  // k = c*9 + tap
+    wsm[i] = a.w[size_t(f) * kw + k];
+  }
+  for (int i = threadIdx.x; i < F; i += blockDim.x) wsm[kw * F + i] = a.bias ? a.bias[i] : 0.0f;
+  __syncthreads();
+  const size_t hw = size_t(a.height) * a.width;
+  const size_t pix = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= hw * a.batch) return;
+  const int b = int(pix / hw);
+  const int rem = int(pix - size_t(b) * hw);
+  const int y = rem / a.width, x = rem - y * a.width;
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = wsm[kw * F + f];
+  for (int c = 0; c < a.cin; ++c) {
+    const float* ip = a.in + (size_t(b) * a.cin + c) * hw;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x + dx - 1;
+        float v = 0.0f;
+        if (yy >= 0 && yy < a.height && xx >= 0 && xx < a.width) v = __ldg(ip + size_t(yy) * a.width + xx);
+        const float* wp = wsm + (c * 9 + dy * 3 + dx) * F;
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(v, wp[f], acc[f]);
+      }
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ctot + a.out_coff);
+#pragma unroll
+  for (int q = 0; q < F / 8; ++q) op[q] = pack8(acc + q * 8);
+  if (a.out2 != nullptr) {
+    uint4* op2 = reinterpret_cast<uint4*>(a.out2 + pix * a.out2_ctot + a.out2_coff);
+#pragma unroll
+    for (int q = 0; q < F / 8; ++q) op2[q] = pack8(acc + q * 8);
+  }
+}
+
+// ------------------------------------------------------------------------------ conv_last
+struct ConvLastArgs {
+  const __nv_bfloat16* in; int in_ctot, in_coff;  // NHWC bf16 window of F channels
+  const float* w;     // fp32 OIHW [cout][F][3][3]
+  const float* bias;  // fp32 [cout]
+  const float* residual;  // optional fp32 NCHW [B][cout][H][W] (DN: the network input)
+  float* out;         // fp32 NCHW [B][cout][H][W], clamped to [0,1] when clamp != 0
+  float* pre;         // optional: un-clamped value (needed by the backward clamp mask)
+  int batch, cout, height, width;
+  int clamp;
+};
+
+template <int F>
+__global__ void __launch_bounds__(128) conv_last_kernel(const ConvLastArgs a) {
+  extern __shared__ float wsm[];  // [cout][9][F]
+  for (int i = threadIdx.x; i < a.cout * 9 * F; i += blockDim.x) {
+    const int f = i % F, t = (i / F) % 9, o = i / (9 * F);
+    wsm[i] = a.w[(size_t(o) * F + f) * 9 + t];
+  }
+  __syncthreads();
+  const size_t hw = size_t(a.height) * a.width;
+  const size_t pix = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= hw * a.batch) return;
+  const int b = int(pix / hw);
+  const int rem = int(pix - size_t(b) * hw);
+  const int y = rem / a.width, x = rem - y * a.width;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    if (yy < 0 || yy >= a.height) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int xx = x + dx - 1;
+      if (xx < 0 || xx >= a.width) continue;
+      const uint4* ip = reinterpret_cast<const uint4*>(a.in + ((size_t(b) * a.height + yy) * a.width + xx) * a.in_ctot + a.in_coff);
+#pragma unroll
+      for (int q = 0; q < F / 8; ++q) {
+        float v[8];
+        unpack8(__ldg(ip + q), v);
+        for (int o = 0; o < a.cout; ++o) {
+          const float* wp = wsm + (o * 9 + dy * 3 + dx) * F + q * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[o] = fmaf(v[i], wp[i], acc[o]);
+        }
+      }
+    }
+  }
+  for (int o = 0; o < a.cout; ++o) {
+    const size_t oi = (size_t(b) * a.cout + o) * hw + rem;
+    float v = acc[o] + (a.bias ? a.bias[o] : 0.0f);
+    if (a.residual != nullptr) v += a.residual[oi];
+    if (a.pre != nullptr) a.pre[oi] = v;
+    a.out[oi] = a.clamp ? fminf(fmaxf(v, 0.0f), 1.0f) : v;
+  }
+}
+
+}  // namespace xmm

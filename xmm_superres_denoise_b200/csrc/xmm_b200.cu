@@ -4,6 +4,7 @@
 #include <unordered_map>
 
 #include "conv3x3_tc.cuh"
+#include "edge_kernels.cuh"
 #include "host_common.cuh"
 #include "pack_weights.cuh"
 
@@ -170,4 +171,122 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   XMM_CONV_CASE(64, 256)
 #undef XMM_CONV_CASE
   return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3: no kernel for kc=%d cout=%d", p.kc, p.cout);
+}
+
+// ----------------------------------------------------------------------------- transforms
+extern "C" int xmm_normalize(const xmm_normalize_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "normalize: null params");
+  const xmm_normalize_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  if (p.n == 0) return XMM_OK;
+  XMM_REQUIRE(p.in && p.out, "normalize: null tensor pointer");
+  XMM_REQUIRE(p.stretch_mode >= 0 && p.stretch_mode <= 3, "normalize: Stretching function %d is not implemented",
+              p.stretch_mode);
+  XMM_REQUIRE((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
+              "normalize: pointers must be 16-byte aligned");
+  XMM_REQUIRE(!p.mask || p.mask_n > 0, "normalize: mask_n must be > 0 with a mask");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NormalizeArgs a{};
+  a.in = p.in; a.mask = p.mask; a.out = p.out; a.n = p.n; a.mask_n = p.mask_n; a.in_is_int32 = p.in_is_int32;
+  a.pre_scale = p.pre_scale; a.max_val = p.max_val; a.mode = p.stretch_mode; a.dyn_max = p.scratch;
+  if (!(p.max_val > 0.0f)) {
+    XMM_REQUIRE(p.scratch != nullptr && !p.in_is_int32 && p.mask == nullptr,
+                "normalize: the max_val <= 0 branch needs fp32 input, no mask and a scratch float");
+    XMM_CUDA_OK(cudaMemsetAsync(p.scratch, 0, sizeof(float), s));
+    max_kernel<<<dev.sm_count * 4, 256, 0, s>>>(static_cast<const float*>(p.in), p.n, p.pre_scale, p.scratch);
+    XMM_CUDA_OK(cudaGetLastError());
+  }
+  const size_t threads = (p.n + 3) / 4;
+  normalize_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>(a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_denormalize(const float* in, float* out, size_t n, size_t per_image, const float* max_vals_dev,
+                               int max_n, int stretch_mode, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  if (n == 0) return XMM_OK;
+  XMM_REQUIRE(in && out && max_vals_dev, "denormalize: null tensor pointer");
+  XMM_REQUIRE(stretch_mode >= 0 && stretch_mode <= 3, "denormalize: Stretching function %d is not implemented",
+              stretch_mode);
+  XMM_REQUIRE(max_n == 1 || (per_image > 0 && size_t(max_n) * per_image == n),
+              "denormalize: %d max values do not match %zu elements of %zu per image", max_n, n, per_image);
+  denormalize_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, n, per_image ? per_image : n, max_vals_dev, max_n, stretch_mode);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_image_upsample(const float* in, float* out, int n_img, int h, int w, int scale, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(scale >= 1, "image_upsample: scale factor %d must be a positive integer", scale);
+  const size_t n_out = size_t(n_img) * h * w * scale * scale;
+  if (n_out == 0) return XMM_OK;
+  XMM_REQUIRE(in && out, "image_upsample: null tensor pointer");
+  image_upsample_kernel<<<unsigned((n_out + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n_out,
+                                                                                                   h, w, scale);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+// ----------------------------------------------------------------------------- first / last conv
+extern "C" int xmm_conv_first(const xmm_conv_first_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "conv_first: null params");
+  const xmm_conv_first_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.in && p.weight && p.out, "conv_first: null tensor pointer");
+  XMM_REQUIRE(p.cin >= 1 && p.cin <= 4, "conv_first: in_channels=%d not in 1..4", p.cin);
+  XMM_REQUIRE(p.batch > 0 && p.height > 0 && p.width > 0, "conv_first: bad shape");
+  XMM_REQUIRE(p.out_ctot % 8 == 0 && p.out_coff % 8 == 0 && p.out_coff + p.filters <= p.out_ctot,
+              "conv_first: output channel window");
+  XMM_REQUIRE(!p.out2 || (p.out2_ctot % 8 == 0 && p.out2_coff % 8 == 0 && p.out2_coff + p.filters <= p.out2_ctot),
+              "conv_first: second output channel window");
+  ConvFirstArgs a{};
+  a.in = p.in; a.w = p.weight; a.bias = p.bias;
+  a.out = static_cast<__nv_bfloat16*>(p.out); a.out_ctot = p.out_ctot; a.out_coff = p.out_coff;
+  a.out2 = static_cast<__nv_bfloat16*>(p.out2); a.out2_ctot = p.out2_ctot; a.out2_coff = p.out2_coff;
+  a.batch = p.batch; a.cin = p.cin; a.height = p.height; a.width = p.width;
+  const size_t npix = size_t(p.batch) * p.height * p.width;
+  const unsigned grid = unsigned((npix + 127) / 128);
+  const size_t smem = (size_t(p.cin) * 9 + 1) * p.filters * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.filters == 32) conv_first_kernel<32><<<grid, 128, smem, s>>>(a);
+  else if (p.filters == 64) conv_first_kernel<64><<<grid, 128, smem, s>>>(a);
+  else return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv_first: filters=%d (supported: 32, 64)", p.filters);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_conv_last(const xmm_conv_last_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "conv_last: null params");
+  const xmm_conv_last_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.in && p.weight && p.out, "conv_last: null tensor pointer");
+  XMM_REQUIRE(p.cout >= 1 && p.cout <= 4, "conv_last: out_channels=%d not in 1..4", p.cout);
+  XMM_REQUIRE(p.batch > 0 && p.height > 0 && p.width > 0, "conv_last: bad shape");
+  XMM_REQUIRE(p.in_ctot % 8 == 0 && p.in_coff % 8 == 0 && p.in_coff + p.filters <= p.in_ctot,
+              "conv_last: input channel window");
+  ConvLastArgs a{};
+  a.in = static_cast<const __nv_bfloat16*>(p.in); a.in_ctot = p.in_ctot; a.in_coff = p.in_coff;
+  a.w = p.weight; a.bias = p.bias; a.residual = p.residual; a.out = p.out; a.pre = p.pre;
+  a.batch = p.batch; a.cout = p.cout; a.height = p.height; a.width = p.width; a.clamp = p.clamp;
+  const size_t npix = size_t(p.batch) * p.height * p.width;
+  const unsigned grid = unsigned((npix + 127) / 128);
+  const size_t smem = size_t(p.cout) * 9 * p.filters * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.filters == 32) conv_last_kernel<32><<<grid, 128, smem, s>>>(a);
+  else if (p.filters == 64) conv_last_kernel<64><<<grid, 128, smem, s>>>(a);
+  else return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv_last: filters=%d (supported: 32, 64)", p.filters);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
 }

@@ -1,0 +1,299 @@
+"""Execution engine behind ``GeneratorRRDB_DN`` / ``GeneratorRRDB_SR``.
+
+Owns what the reference leaves to autograd and cuDNN:
+
+* the packed bf16 weight images of every 3x3 layer (rebuilt by ONE kernel launch whenever a
+  parameter changes -- after ``optimizer.step()`` or ``load_state_dict``),
+* the NHWC bf16 activation buffers: one ``5*F``-channel buffer per dense block, so that
+  ``torch.cat`` (rrdb_blocks.py:49-52) is a channel offset,
+* the launch sequence of the forward pass (and, in ``engine_train.py``, the backward pass).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from ._lib import PackJob
+
+_ALIGN = 1024
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class _Segment:
+    param: torch.Tensor
+    src_cin: int
+    o_off: int
+    i_off: int
+    transpose: int
+    k_off: int
+    k_count: int
+    scale: float
+
+
+@dataclass
+class _Blob:
+    """One packed layer: `nt` GEMM columns (output channels), K = nchunks*kc input channels."""
+    name: str
+    nt: int
+    kc: int
+    nchunks: int
+    segments: List[_Segment]
+    bias: Optional[torch.Tensor] = None
+    perm: int = 0
+    offset: int = 0  # byte offset inside the blob arena
+
+    @property
+    def nbytes(self) -> int:
+        return self.nchunks * 9 * self.nt * self.kc * 2 + self.nt * 4
+
+
+class WeightArena:
+    """All packed layers of one model in one device buffer + the device-side job table."""
+
+    def __init__(self) -> None:
+        self.blobs: Dict[str, _Blob] = {}
+        self._order: List[_Blob] = []
+        self._arena: Optional[torch.Tensor] = None
+        self._jobs_dev: Optional[torch.Tensor] = None
+        self._key: Optional[tuple] = None
+        self._versions: Optional[tuple] = None
+
+    def add(self, blob: _Blob) -> None:
+        if blob.name in self.blobs:
+            raise KeyError(blob.name)
+        self.blobs[blob.name] = blob
+        self._order.append(blob)
+
+    def ptr(self, name: str) -> int:
+        assert self._arena is not None
+        return self._arena.data_ptr() + self.blobs[name].offset
+
+    def _params(self) -> List[torch.Tensor]:
+        ps = []
+        for b in self._order:
+            ps.extend(s.param for s in b.segments)
+            if b.bias is not None:
+                ps.append(b.bias)
+        return ps
+
+    def ensure(self, device: torch.device) -> None:
+        """(Re)build the job table if parameter storage moved; re-pack if any parameter changed."""
+        params = self._params()
+        key = (str(device),) + tuple(p.data_ptr() for p in params)
+        if key != self._key:
+            off = 0
+            for b in self._order:
+                b.offset = off
+                off = _round_up(off + b.nbytes, _ALIGN)
+            self._arena = torch.empty(off, dtype=torch.uint8, device=device)
+            jobs = (PackJob * len(self._order))()
+            for j, b in zip(jobs, self._order):
+                j.dst = self._arena.data_ptr() + b.offset
+                j.bias = b.bias.data_ptr() if b.bias is not None else None
+                j.nt, j.kc, j.nchunks, j.nseg, j.perm, j.n_valid = b.nt, b.kc, b.nchunks, len(b.segments), b.perm, b.nt
+                for s_c, s in zip(j.seg, b.segments):
+                    if s.param.dtype != torch.float32 or not s.param.is_contiguous() or s.param.device != device:
+                        raise RuntimeError(f"{b.name}: parameters must be contiguous fp32 tensors on {device}")
+                    s_c.src, s_c.src_cin, s_c.o_off, s_c.i_off = s.param.data_ptr(), s.src_cin, s.o_off, s.i_off
+                    s_c.transpose, s_c.k_off, s_c.k_count, s_c.scale = s.transpose, s.k_off, s.k_count, s.scale
+            raw = bytes(jobs)
+            self._jobs_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+            self._key = key
+            self._versions = None
+        versions = tuple(p._version for p in params)
+        if versions != self._versions:
+            _lib.check(_lib.load().xmm_pack_weights(self._jobs_dev.data_ptr(), len(self._order), _lib.stream_ptr()))
+            self._versions = versions
+
+
+def _fwd_blob(name: str, conv: nn.Conv2d, kc: int, perm: int = 0) -> _Blob:
+    cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+    return _Blob(name, cout, kc, cin // kc,
+                 [_Segment(conv.weight, cin, 0, 0, 0, 0, cin, 1.0)], conv.bias, perm)
+
+
+class RRDBEngine:
+    """Forward pass of the RRDB generators on the tensor-core kernels (inference half)."""
+
+    def __init__(self, gen: nn.Module, kind: str) -> None:
+        self.kind = kind
+        self.nf = gen.num_filters
+        self.nb = gen.num_res_blocks
+        if self.nf not in (32, 64):
+            raise NotImplementedError(
+                f"num_filters={self.nf}: the sm_100a kernels are built for 32 or 64 filters (no fallback path)")
+        self.kc = 32 if self.nf == 32 else 64
+        self.num_upsample = getattr(gen, "num_upsample", 0)
+        self._gen_ref = [gen]  # no nn.Module registration (avoid a reference cycle in the module tree)
+        self.arena = WeightArena()
+        g = gen
+        for i, rrdb in enumerate(g.rrdb):
+            for r, rdb in enumerate((rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)):
+                for k in range(1, 6):
+                    self.arena.add(_fwd_blob(f"f.{i}.{r}.{k}", getattr(rdb, f"conv{k}"), self.kc))
+        self.arena.add(_fwd_blob("f.trunk", g.trunk_conv, self.kc))
+        if kind == "sr":
+            for s in range(self.num_upsample):
+                self.arena.add(_fwd_blob(f"f.up{s}", g.upsampling[3 * s], self.kc, perm=1))
+            self.arena.add(_fwd_blob("f.hr", g.HRconv, self.kc))
+        self._bufs: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+    @property
+    def gen(self) -> nn.Module:
+        return self._gen_ref[0]
+
+    # ------------------------------------------------------------------ buffers
+    def _inference_buffers(self, b: int, h: int, w: int, device: torch.device) -> Dict[str, torch.Tensor]:
+        key = ("inf", b, h, w, str(device))
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            self._bufs.clear()  # one live shape at a time: these are multi-GB at batch 64
+            f = self.nf
+            bufs = {f"rdb{r}": torch.empty(b, h, w, 5 * f, dtype=torch.bfloat16, device=device) for r in range(3)}
+            bufs["fea"] = torch.empty(b, h, w, f, dtype=torch.bfloat16, device=device)
+            bufs["trunk"] = torch.empty(b, h, w, f, dtype=torch.bfloat16, device=device)
+            hh, ww = h, w
+            for s in range(self.num_upsample if self.kind == "sr" else 0):
+                hh, ww = 2 * hh, 2 * ww
+                bufs[f"up{s}"] = torch.empty(b, hh, ww, f, dtype=torch.bfloat16, device=device)
+            if self.kind == "sr":
+                bufs["hr"] = torch.empty(b, hh, ww, f, dtype=torch.bfloat16, device=device)
+            self._bufs[key] = bufs
+        return bufs
+
+    # ------------------------------------------------------------------ dense blocks
+    def _rdb_forward(self, name: str, buf: torch.Tensor, out: torch.Tensor, *, s0: float, s1: float,
+                     r2: Optional[torch.Tensor], s2: float) -> None:
+        """One ResidualDenseBlock_5C (rrdb_blocks.py:37-54): x in buf[..., :F]; result -> out[..., :F]."""
+        f, kc, a = self.nf, self.kc, self.arena
+        for k in range(1, 5):
+            ops.conv3x3(buf, 0, k * f, a.ptr(f"{name}.{k}"), kc, f, buf, k * f, lrelu=0.2)
+        ops.conv3x3(buf, 0, 5 * f, a.ptr(f"{name}.5"), kc, f, out, 0, s0=s0, r1=buf, r1_coff=0, s1=s1,
+                    r2=r2, r2_coff=0, s2=s2)
+
+    def _trunk_forward(self, x: torch.Tensor, rdb_bufs: List[torch.Tensor], fea: torch.Tensor,
+                       trunk_out: torch.Tensor) -> None:
+        """_GeneratorRRDB.forward (generator_rrdb.py:66-69).  rdb_bufs: 3 buffers (ping-pong, inference)
+        or 3*nb + 1 buffers (training: every dense block keeps its activations)."""
+        g, f = self.gen, self.nf
+        ring = len(rdb_bufs)
+        keep_all = ring > 3
+        first = rdb_bufs[0]
+        if keep_all:
+            ops.conv_first(x, g.conv_first.weight, g.conv_first.bias, first, 0)
+            fea = first  # RDB 0's input window is never overwritten in training
+        else:
+            ops.conv_first(x, g.conv_first.weight, g.conv_first.bias, first, 0, out2=fea, out2_coff=0)
+        idx = 0
+        for i in range(self.nb):
+            x_rrdb = rdb_bufs[idx % ring]
+            for r in range(3):
+                cur = rdb_bufs[idx % ring]
+                nxt = rdb_bufs[(idx + 1) % ring]
+                if r < 2:
+                    # x5 * 0.2 + x
+                    self._rdb_forward(f"f.{i}.{r}", cur, nxt, s0=0.2, s1=1.0, r2=None, s2=0.0)
+                else:
+                    # (x5 * 0.2 + x_rdb3) * 0.2 + x_rrdb   (rrdb_blocks.py:54,70)
+                    self._rdb_forward(f"f.{i}.{r}", cur, nxt, s0=0.04, s1=0.2, r2=x_rrdb, s2=1.0)
+                idx += 1
+        last = rdb_bufs[idx % ring]
+        ops.conv3x3(last, 0, f, self.arena.ptr("f.trunk"), self.kc, f, trunk_out, 0, s0=1.0, r1=fea, r1_coff=0, s1=1.0)
+
+    # ------------------------------------------------------------------ public
+    def _check_input(self, x: torch.Tensor) -> None:
+        g = self.gen
+        if x.dim() != 4 or x.shape[1] != g.in_channels:
+            raise RuntimeError(f"expected input (B,{g.in_channels},H,W), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("xmm_superres_denoise_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if g.in_channels > 4 or g.out_channels > 4:
+            raise NotImplementedError("in_channels / out_channels above 4 are not built")
+        for p in g.parameters():
+            if p.device != x.device or p.dtype != torch.float32:
+                raise RuntimeError("model parameters must be fp32 and on the input's device")
+
+    @torch.no_grad()
+    def forward_inference(self, x: torch.Tensor) -> torch.Tensor:
+        self._check_input(x)
+        g = self.gen
+        x = x.contiguous().float()
+        b, _, h, w = x.shape
+        self.arena.ensure(x.device)
+        bufs = self._inference_buffers(b, h, w, x.device)
+        self._trunk_forward(x, [bufs["rdb0"], bufs["rdb1"], bufs["rdb2"]], bufs["fea"], bufs["trunk"])
+        if self.kind == "dn":
+            if g.in_channels != g.out_channels:
+                raise RuntimeError("GeneratorRRDB_DN adds its input to its output: in_channels must equal out_channels")
+            out = torch.empty(b, g.out_channels, h, w, dtype=torch.float32, device=x.device)
+            ops.conv_last(bufs["trunk"], 0, g.conv_last.weight, g.conv_last.bias, out, residual=x, clamp=True)
+            return out
+        cur = bufs["trunk"]
+        for s in range(self.num_upsample):
+            ops.conv3x3(cur, 0, self.nf, self.arena.ptr(f"f.up{s}"), self.kc, 4 * self.nf, bufs[f"up{s}"], 0,
+                        lrelu=0.01, pixel_shuffle=True)
+            cur = bufs[f"up{s}"]
+        ops.conv3x3(cur, 0, self.nf, self.arena.ptr("f.hr"), self.kc, self.nf, bufs["hr"], 0, lrelu=0.2)
+        hh, ww = cur.shape[1], cur.shape[2]
+        out = torch.empty(b, g.out_channels, hh, ww, dtype=torch.float32, device=x.device)
+        ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, clamp=True)
+        return out
+
+
+# ---------------------------------------------------------------------- standalone blocks
+class _BlockRunner:
+    """RRDB / ResidualDenseBlock_5C called on their own (reference exports them from
+    models/modules/__init__.py:1).  Inference only."""
+
+    def __init__(self, rdbs) -> None:
+        nf, gc = rdbs[0].nf, rdbs[0].gc
+        if nf != gc or nf not in (32, 64):
+            raise NotImplementedError(f"standalone dense block with nf={nf}, gc={gc}: only nf == gc in (32, 64) is built")
+        self.nf, self.kc = nf, (32 if nf == 32 else 64)
+        self.arena = WeightArena()
+        for r, rdb in enumerate(rdbs):
+            for k in range(1, 6):
+                self.arena.add(_fwd_blob(f"{r}.{k}", getattr(rdb, f"conv{k}"), self.kc))
+        self.n = len(rdbs)
+
+    def run(self, x: torch.Tensor, rrdb: bool) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("xmm_superres_denoise_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        f, kc = self.nf, self.kc
+        b, c, h, w = x.shape
+        if c != f:
+            raise RuntimeError(f"expected {f} channels, got {c}")
+        self.arena.ensure(x.device)
+        bufs = [torch.empty(b, h, w, 5 * f, dtype=torch.bfloat16, device=x.device) for _ in range(self.n + 1)]
+        bufs[0][..., :f] = x.permute(0, 2, 3, 1)
+        for r in range(self.n):
+            last = rrdb and r == self.n - 1
+            cur, nxt = bufs[r], bufs[r + 1]
+            for k in range(1, 5):
+                ops.conv3x3(cur, 0, k * f, self.arena.ptr(f"{r}.{k}"), kc, f, cur, k * f, lrelu=0.2)
+            ops.conv3x3(cur, 0, 5 * f, self.arena.ptr(f"{r}.5"), kc, f, nxt, 0, s0=0.04 if last else 0.2, r1=cur,
+                        r1_coff=0, s1=0.2 if last else 1.0, r2=bufs[0] if last else None, r2_coff=0,
+                        s2=1.0 if last else 0.0)
+        return bufs[self.n][..., :f].permute(0, 3, 1, 2).float().contiguous()
+
+
+def standalone_block_forward(rdbs, x: torch.Tensor, rrdb: bool) -> torch.Tensor:
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for m in rdbs for p in m.parameters())):
+        raise NotImplementedError(
+            "autograd through a standalone RRDB / ResidualDenseBlock_5C is not built; use GeneratorRRDB_SR/DN "
+            "(whole-generator backward) or wrap the call in torch.no_grad()")
+    runner = rdbs[0].__dict__.get("_xmm_runner")
+    if runner is None or runner.n != len(rdbs):
+        runner = _BlockRunner(rdbs)
+        rdbs[0].__dict__["_xmm_runner"] = runner
+    with torch.no_grad():
+        return runner.run(x, rrdb)

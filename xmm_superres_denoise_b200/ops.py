@@ -1,0 +1,152 @@
+"""Thin Python wrappers over the C ABI: one function per kernel family.
+
+Tensors are torch CUDA tensors used purely as device-memory handles; activations are NHWC
+bf16 ``[B, H, W, C]`` and a convolution reads / writes a *channel window* of them.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Conv3x3Params, ConvFirstParams, ConvLastParams, NormalizeParams
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _nhwc(t: torch.Tensor, name: str) -> None:
+    _lib.require_cuda_tensor(t, torch.bfloat16, name)
+    if t.dim() != 4:
+        raise RuntimeError(f"{name}: expected [B,H,W,C], got {tuple(t.shape)}")
+
+
+def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, cout: int,
+            out: torch.Tensor, out_coff: int, *, lrelu: float = 1.0, s0: float = 1.0,
+            r1: Optional[torch.Tensor] = None, r1_coff: int = 0, s1: float = 0.0,
+            r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
+            mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
+            pixel_shuffle: bool = False, tap_mode: int = 0) -> None:
+    """out[..., out_coff:out_coff+cout] = epilogue(conv3x3(inp[..., in_coff:in_coff+cin])).
+
+    See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
+    _nhwc(inp, "conv3x3 input")
+    _nhwc(out, "conv3x3 output")
+    b, h, w, ctot = inp.shape
+    p = Conv3x3Params()
+    p.in_, p.in_ctot, p.in_coff, p.cin = inp.data_ptr(), ctot, in_coff, cin
+    p.wblob, p.kc, p.cout = wblob_ptr, kc, cout
+    p.batch, p.height, p.width = b, h, w
+    p.lrelu_slope = lrelu
+    if mask is not None:
+        _nhwc(mask, "conv3x3 mask")
+        p.mask, p.mask_ctot, p.mask_coff = mask.data_ptr(), mask.shape[3], mask_coff
+    p.mask_slope = mask_slope
+    p.s0 = s0
+    if r1 is not None:
+        _nhwc(r1, "conv3x3 r1")
+        p.r1, p.r1_ctot, p.r1_coff = r1.data_ptr(), r1.shape[3], r1_coff
+    p.s1 = s1
+    if r2 is not None:
+        _nhwc(r2, "conv3x3 r2")
+        p.r2, p.r2_ctot, p.r2_coff = r2.data_ptr(), r2.shape[3], r2_coff
+    p.s2 = s2
+    exp = (b, 2 * h, 2 * w) if pixel_shuffle else (b, h, w)
+    if tuple(out.shape[:3]) != exp:
+        raise RuntimeError(f"conv3x3 output: expected spatial shape {exp}, got {tuple(out.shape[:3])}")
+    p.out, p.out_ctot, p.out_coff = out.data_ptr(), out.shape[3], out_coff
+    p.pixel_shuffle = 1 if pixel_shuffle else 0
+    p.tap_mode = tap_mode
+    _lib.check(_lib.load().xmm_conv3x3_bf16(ctypes.byref(p), _lib.stream_ptr()))
+
+
+def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+               out_coff: int, out2: Optional[torch.Tensor] = None, out2_coff: int = 0) -> None:
+    """fp32 NCHW image -> bf16 NHWC features (generator_rrdb.py:31-37,67)."""
+    _lib.require_cuda_tensor(x, torch.float32, "conv_first input")
+    _lib.require_cuda_tensor(weight, torch.float32, "conv_first weight")
+    _nhwc(out, "conv_first output")
+    b, cin, h, w = x.shape
+    p = ConvFirstParams()
+    p.in_, p.weight, p.bias = x.data_ptr(), weight.data_ptr(), _ptr(bias)
+    p.batch, p.cin, p.height, p.width, p.filters = b, cin, h, w, weight.shape[0]
+    p.out, p.out_ctot, p.out_coff = out.data_ptr(), out.shape[3], out_coff
+    if out2 is not None:
+        _nhwc(out2, "conv_first output2")
+        p.out2, p.out2_ctot, p.out2_coff = out2.data_ptr(), out2.shape[3], out2_coff
+    _lib.check(_lib.load().xmm_conv_first(ctypes.byref(p), _lib.stream_ptr()))
+
+
+def conv_last(inp: torch.Tensor, in_coff: int, weight: torch.Tensor, bias: Optional[torch.Tensor],
+              out: torch.Tensor, residual: Optional[torch.Tensor] = None, pre: Optional[torch.Tensor] = None,
+              clamp: bool = True) -> None:
+    """bf16 NHWC features -> fp32 NCHW image (+ residual, clamp) (generator_rrdb.py:48-54,107-108,132-135)."""
+    _nhwc(inp, "conv_last input")
+    _lib.require_cuda_tensor(weight, torch.float32, "conv_last weight")
+    _lib.require_cuda_tensor(out, torch.float32, "conv_last output")
+    b, h, w, ctot = inp.shape
+    p = ConvLastParams()
+    p.in_, p.in_ctot, p.in_coff = inp.data_ptr(), ctot, in_coff
+    p.weight, p.bias = weight.data_ptr(), _ptr(bias)
+    if residual is not None:
+        _lib.require_cuda_tensor(residual, torch.float32, "conv_last residual")
+        if residual.shape != out.shape:
+            raise RuntimeError("conv_last residual: shape must equal the output shape")
+        p.residual = residual.data_ptr()
+    if pre is not None:
+        _lib.require_cuda_tensor(pre, torch.float32, "conv_last pre")
+        p.pre = pre.data_ptr()
+    p.out = out.data_ptr()
+    p.batch, p.cout, p.height, p.width, p.filters = b, weight.shape[0], h, w, weight.shape[1]
+    p.clamp = 1 if clamp else 0
+    _lib.check(_lib.load().xmm_conv_last(ctypes.byref(p), _lib.stream_ptr()))
+
+
+def normalize(inp: torch.Tensor, max_val: float, stretch_mode: str, *, out: Optional[torch.Tensor] = None,
+              mask: Optional[torch.Tensor] = None, pre_scale: float = 1.0) -> torch.Tensor:
+    """Fused clamp / divide / stretch / clamp (+ detector mask, + counts->rate scale)."""
+    if stretch_mode not in _lib.STRETCH_MODES:
+        raise ValueError(f"Stretching function {stretch_mode} is not implemented")
+    if not inp.is_cuda or not inp.is_contiguous() or inp.dtype not in (torch.float32, torch.int32):
+        raise RuntimeError("normalize: expected a contiguous CUDA fp32 or int32 tensor")
+    if out is None:
+        out = torch.empty(inp.shape, dtype=torch.float32, device=inp.device)
+    _lib.require_cuda_tensor(out, torch.float32, "normalize output")
+    p = NormalizeParams()
+    p.in_, p.in_is_int32 = inp.data_ptr(), int(inp.dtype == torch.int32)
+    if mask is not None:
+        _lib.require_cuda_tensor(mask, torch.uint8, "normalize mask")
+        p.mask, p.mask_n = mask.data_ptr(), mask.numel()
+    p.out, p.n = out.data_ptr(), inp.numel()
+    p.pre_scale, p.max_val, p.stretch_mode = pre_scale, float(max_val), _lib.STRETCH_MODES[stretch_mode]
+    scratch = None
+    if not max_val > 0:
+        scratch = torch.zeros(1, dtype=torch.float32, device=inp.device)
+        p.scratch = scratch.data_ptr()
+    _lib.check(_lib.load().xmm_normalize(ctypes.byref(p), _lib.stream_ptr()))
+    return out
+
+
+def denormalize(inp: torch.Tensor, max_vals: torch.Tensor, stretch_mode: str) -> torch.Tensor:
+    if stretch_mode not in _lib.STRETCH_MODES:
+        raise ValueError(f"Stretching function {stretch_mode} is not implemented")
+    _lib.require_cuda_tensor(inp, torch.float32, "denormalize input")
+    mv = max_vals.to(device=inp.device, dtype=torch.float32).reshape(-1).contiguous()
+    out = torch.empty_like(inp)
+    per_image = inp.numel() // inp.shape[0] if inp.dim() > 0 and inp.shape[0] > 0 else inp.numel()
+    _lib.check(_lib.load().xmm_denormalize(inp.data_ptr(), out.data_ptr(), inp.numel(), per_image, mv.data_ptr(),
+                                           mv.numel(), _lib.STRETCH_MODES[stretch_mode], _lib.stream_ptr()))
+    return out
+
+
+def image_upsample(x: torch.Tensor, scale: int) -> torch.Tensor:
+    """Nearest upsample by an integer factor, divided by factor**2 (imageupsample.py:10-26)."""
+    _lib.require_cuda_tensor(x, torch.float32, "image_upsample input")
+    h, w = x.shape[-2:]
+    n_img = x.numel() // (h * w) if h * w else 0
+    out = torch.empty(*x.shape[:-2], h * scale, w * scale, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().xmm_image_upsample(x.data_ptr(), out.data_ptr(), n_img, h, w, scale, _lib.stream_ptr()))
+    return out
