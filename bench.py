@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: BASELINE.json configs[1] -- XMM-SuperRes 2x RRDB inference, synthetic batch
+64 of single-channel 416x416 count images per GPU, images/sec (weak scaling: every GPU runs its own
+batch of 64, no collective -- SURVEY.md section 8e).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload infer_sr|train_dn]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0 (contract in the task statement): `value` is device-resident
+throughput, `e2e` the same metric through the public classes with pinned HOST buffers (H2D of the
+int32 counts + fused normalise + generator + D2H of the fp32 prediction inside the timed region),
+`roofline` the tensor-core fraction of the dominant kernel (dense-block conv3x3) from CUDA events
+recorded around every one of its launches in the timed region, `cpu_baseline` the oracle port
+(torch fp32 on the host cores) on a bounded sample.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+LR_MAX, HR_MAX_SR = 0.0022336, 0.0005584  # res/baseline_config.toml:35,42
+NF, NB = 32, 4  # res/configs/models.toml:5-6
+BATCH_INFER = 64
+METRIC = "RRDB SR-2x inference images/sec (F=32, nb=4, 416x416 -> 832x832, batch 64 per GPU)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "src": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index: int) -> None:
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self._nv, self._err = None, repr(e)
+
+    def _run(self) -> None:
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable: " + getattr(self, "_err", "no samples")]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ workload
+def synthetic_counts(batch: int, seed: int, kind: str):
+    """(lr int32 [B,1,416,416], hr int32, t_lr, t_hr): a few generated images tiled to the batch."""
+    from oracle.synthetic import count_batch
+
+    uniq = min(batch, 8)
+    lr, hr, t_lr, t_hr = count_batch(uniq, seed, kind)
+    reps = (batch + uniq - 1) // uniq
+    return np.tile(lr, (reps, 1, 1, 1))[:batch], np.tile(hr, (reps, 1, 1, 1))[:batch], t_lr, t_hr
+
+
+def conv_flops_sr(nf: int, nb: int, pixels: int):
+    """Algorithmic FLOPs: dense-block convs only / whole SR-2x forward."""
+    dense = 2 * (405 * nb * nf * nf) * pixels
+    total = 2 * (9 * 1 * nf + 405 * nb * nf * nf + 9 * nf * nf + 72 * nf * nf + 36 * nf * 1) * pixels
+    return dense, total
+
+
+def oracle_state_dict(kind: str):
+    from oracle import rrdb_oracle as O
+
+    return O.init_state_dict(kind, 1, 1, NF, NB, 1, seed=21)
+
+
+def cpu_infer_sample(n_images: int, threads: int):
+    """Oracle port (torch fp32 CPU) SR inference incl. normalise; returns images/sec."""
+    from oracle import rrdb_oracle as O
+
+    torch.set_num_threads(threads)
+    sd = oracle_state_dict("sr")
+    lr, _, t_lr, _ = synthetic_counts(1, 7, "sr")
+    x = torch.from_numpy(lr.astype(np.float32))
+    with torch.no_grad():
+        O.model_forward(O.normalize_image(x / t_lr, LR_MAX, "sqrt"), sd, "sr", 1)  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(n_images):
+            O.model_forward(O.normalize_image(x / t_lr, LR_MAX, "sqrt"), sd, "sr", 1)
+        dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(args, rank: int) -> None:
+    """--impl reference: the reference's CPU implementation of the path (oracle port: /root/reference is
+    Python and cannot travel to the GPU box), all host threads, one image per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle import rrdb_oracle as O
+
+    torch.set_num_threads(threads)
+    sd = oracle_state_dict("sr")
+    lr, _, t_lr, _ = synthetic_counts(1, 7, "sr")
+    x = torch.from_numpy(lr.astype(np.float32))
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.model_forward(O.normalize_image(x / t_lr, LR_MAX, "sqrt"), sd, "sr", 1)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: XMM-SuperRes 2x RRDB inference (F=32, nb=4), CPU fp32",
+                       "sample": "1 image of 416x416 per step (bounded sample of the batch-64 workload)"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps x 1 image, torch {torch.__version__} fp32 oneDNN"},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_INFER)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; xmm_superres_denoise_b200 has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: PLC0415
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from xmm_superres_denoise_b200 import _lib, ops
+    from xmm_superres_denoise_b200.models import GeneratorRRDB_SR
+    from xmm_superres_denoise_b200.transforms import Normalize
+
+    _lib.check(_lib.load().xmm_check_device())
+    B = args.batch
+    model = GeneratorRRDB_SR(1, 1, NF, NB, num_upsample=1)
+    model.load_state_dict(oracle_state_dict("sr"))
+    model = model.to(dev).eval()
+    norm = Normalize(LR_MAX, HR_MAX_SR, "sqrt")
+    lr_np, _, t_lr, _ = synthetic_counts(B, 1234 + rank, "sr")
+    counts_host = torch.from_numpy(lr_np).pin_memory()
+    out_host = torch.empty(B, 1, 832, 832, dtype=torch.float32).pin_memory()
+    counts_dev = counts_host.to(dev)
+    x_dev = norm.normalize_counts(counts_dev, norm.lr_max, exposure=t_lr)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing
+    prof_events = []
+    orig_conv = ops.conv3x3
+
+    def conv_profiled(inp, in_coff, cin, wptr, kc, cout, out, out_coff, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_conv(inp, in_coff, cin, wptr, kc, cout, out, out_coff, **kw)
+        e1.record()
+        if cout == NF and inp.shape[3] == 5 * NF:  # dense-block layers = the dominant kernel instantiation
+            prof_events.append((e0, e1, 2.0 * 9 * cin * cout * inp.shape[0] * inp.shape[1] * inp.shape[2]))
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(x_dev)
+        import xmm_superres_denoise_b200.engine as engine_mod
+
+        engine_mod.ops.conv3x3 = conv_profiled
+        ops.LAUNCHES = 0
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            start.record()
+            for _ in range(args.steps):
+                model(x_dev)
+            stop.record()
+            barrier()
+        engine_mod.ops.conv3x3 = orig_conv
+        launches = ops.LAUNCHES
+        ms_total = start.elapsed_time(stop)
+        k_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in prof_events)
+        k_flop = sum(f for _, _, f in prof_events)
+        n_k = len(prof_events)
+
+        # ------------------------------------------------------------ end to end (host buffers)
+        def e2e_step():
+            c = counts_host.to(dev, non_blocking=True)
+            x = norm.normalize_counts(c, norm.lr_max, exposure=t_lr)
+            y = model(x)
+            out_host.copy_(y, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            e2e_step()
+        t2.record()
+        barrier()
+        e2e_ms = s2.elapsed_time(t2)
+
+    times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = (float(v) for v in times.cpu())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    pixels = B * 416 * 416
+    dense_flop, total_flop = conv_flops_sr(NF, NB, pixels)
+    value = world * B * args.steps / (ms_total * 1e-3)
+    achieved = k_flop / (k_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: XMM-SuperRes 2x RRDB inference, F=32 nb=4, batch %d/GPU of 1x416x416 "
+                               "Poisson count images -> 1x832x832" % B,
+                   "l2": "no flush needed: ~%.0f GB of activations stream per step (>> 126 MB L2)" % (
+                       pixels * (NB * 3 * 21 * NF * 2) / 1e9),
+                   "model_tflop_per_step": total_flop / 1e12},
+        "clocks": clocks.summary(),
+        "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": counts_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<KC=32,NT=32> (dense-block 3x3 convs)",
+                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16_sustained"], "frac_of_burst": achieved / pk["bf16_burst"],
+                     "peak_src": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                     "launches_timed": n_k, "share_of_step": k_ms / ms_total, "traffic": None,
+                     "whole_step_tflops": total_flop * args.steps / (ms_total * 1e-3) / 1e12},
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ips, dt = cpu_infer_sample(8, threads)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "8 images of the same workload (%.1f s), oracle port: torch %s fp32 on CPU" % (
+                                    dt, torch.__version__)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

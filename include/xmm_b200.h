@@ -94,7 +94,8 @@ typedef struct {
   const void* r1; int r1_ctot, r1_coff; float s1;
   const void* r2; int r2_ctot, r2_coff; float s2;
   void* out; int out_ctot, out_coff;
-  int pixel_shuffle;  /* 1: out is [batch][2*height][2*width][out_ctot], cout/4 channels   */
+  int pixel_shuffle;  /* 1: out is [batch][2*height][2*width][out_ctot], cout/4 channels;
+                         2: inverse -- out is [batch][height/2][width/2][out_ctot], 4*cout ch. */
   int tap_mode;       /* 0 = library default; 1..3 force a shared-memory tap layout (probe only) */
 } xmm_conv3x3_params;
 
@@ -143,6 +144,9 @@ typedef struct {
   int batch, cin, height, width, filters;  /* cin 1..4, filters 32 or 64                    */
   void* out; int out_ctot, out_coff;
   void* out2; int out2_ctot, out2_coff;    /* optional second copy (trunk skip), or NULL     */
+  /* Backward use -- the data gradient of conv_last is this same stencil on the loss gradient: */
+  const float* gate;  /* optional, shape of `in`: in is used only where 0 <= gate <= 1 (clamp)   */
+  const void* mask; int mask_ctot, mask_coff; float mask_slope; /* optional LeakyReLU' on out  */
 } xmm_conv_first_params;
 int xmm_conv_first(const xmm_conv_first_params* p, void* stream);
 
@@ -159,6 +163,60 @@ typedef struct {
   int clamp;
 } xmm_conv_last_params;
 int xmm_conv_last(const xmm_conv_last_params* p, void* stream);
+
+/* Weight gradients -------------------------------------------------------------------- */
+/* dW[tap][c][n] = sum_p X[p+off(tap)][c] * dY[p][n] on the tensor cores (autograd's conv
+ * bwd-filter for rrdb_blocks.py:27-31, generator_rrdb.py:39-45,93-101).  The launch is split
+ * into roles (a CTA keeps tap_count*n <= 512 TMEM columns of accumulators for its whole life);
+ * every role streams all pixel tiles; a second kernel reduces the per-CTA partial sums into
+ * the fp32 OIHW gradient tensors listed in dst[].                                           */
+typedef struct {
+  int tap_begin, tap_count; /* taps [tap_begin, tap_begin+tap_count) of the 9, tap = 3*dy+dx   */
+  int x_c0, x_boxes;        /* M tile: X channels [x_c0, x_c0 + 64*x_boxes) (x_boxes 1 or 2)    */
+  int y_c0, n;              /* N tile: dY channels [y_c0, y_c0 + n), n multiple of 16, <= 192   */
+} xmm_wgrad_role;
+
+typedef struct {
+  float* dw;                /* fp32 OIHW [o_count][i_total][3][3]                               */
+  int o_count, i_total;
+  int i_begin, i_end;       /* input channels taken from role `role`                            */
+  int role;
+  int lane0;                /* accumulator row of input channel i_begin ( = i_begin - x_c0 )    */
+  int col0;                 /* accumulator column (within one tap) of output channel 0         */
+  float scale;
+  int accumulate;           /* 0: overwrite dw, 1: add                                          */
+  int perm;                 /* 1: columns are in PixelShuffle-packed order                      */
+} xmm_wgrad_dst;
+
+typedef struct {
+  const void* x; int x_ctot;   /* bf16 NHWC activations                                        */
+  const void* dy; int dy_ctot; /* bf16 NHWC gradients                                          */
+  int batch, height, width;
+  int nroles; xmm_wgrad_role roles[4];
+  int ndst; xmm_wgrad_dst dst[16];
+  float* workspace;            /* xmm_wgrad_workspace_bytes() bytes                            */
+} xmm_wgrad_params;
+
+size_t xmm_wgrad_workspace_bytes(void);
+int xmm_conv3x3_wgrad(const xmm_wgrad_params* p, void* stream);
+
+/* out[i] (+)= scale * sum over pixels of in[p][c0 + i]  (bias gradients), n multiple of 8.  */
+int xmm_colsum_bf16(const void* in, int ctot, int c0, int n, size_t npix, float* out, float scale,
+                    int accumulate, void* stream);
+
+/* Weight/bias gradients of the two CUDA-core convolutions:
+ *   R[o][c][tap] += sum_p s[o][p] * (V[p+off(tap)][c] + V2[p+off(tap)][c]);  S[o] += sum_p s[o][p]
+ * conv_last: s = dL/dout (gated by the clamp), V = input features.  conv_first: s = input
+ * image, V (+V2) = dL/dfea; then dW_first[f][o][8-tap] = R[o][f][tap].                        */
+typedef struct {
+  const float* s; const float* gate;  /* fp32 NCHW [batch][ns][height][width]                  */
+  const void* v; int v_ctot, v_coff;  /* bf16 NHWC, `channels` channels                        */
+  const void* v2; int v2_ctot, v2_coff; /* optional                                            */
+  float* r;                           /* fp32 [ns][channels][9], accumulated into              */
+  float* ssum;                        /* fp32 [ns] or NULL, accumulated into                   */
+  int batch, ns, height, width, channels; /* channels 32 or 64                                 */
+} xmm_edge_wgrad_params;
+int xmm_edge_wgrad(const xmm_edge_wgrad_params* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,9 @@ class ConvFirstParams(Structure):
     _fields_ = [("in_", c_void_p), ("weight", c_void_p), ("bias", c_void_p),
                 ("batch", c_int), ("cin", c_int), ("height", c_int), ("width", c_int), ("filters", c_int),
                 ("out", c_void_p), ("out_ctot", c_int), ("out_coff", c_int),
-                ("out2", c_void_p), ("out2_ctot", c_int), ("out2_coff", c_int)]
+                ("out2", c_void_p), ("out2_ctot", c_int), ("out2_coff", c_int),
+                ("gate", c_void_p), ("mask", c_void_p), ("mask_ctot", c_int), ("mask_coff", c_int),
+                ("mask_slope", c_float)]
 
 
 class ConvLastParams(Structure):
@@ -58,6 +60,33 @@ class ConvLastParams(Structure):
                 ("batch", c_int), ("cout", c_int), ("height", c_int), ("width", c_int), ("filters", c_int),
                 ("clamp", c_int)]
 
+
+class WgradRole(Structure):
+    _fields_ = [("tap_begin", c_int), ("tap_count", c_int), ("x_c0", c_int), ("x_boxes", c_int), ("y_c0", c_int),
+                ("n", c_int)]
+
+
+class WgradDst(Structure):
+    _fields_ = [("dw", c_void_p), ("o_count", c_int), ("i_total", c_int), ("i_begin", c_int), ("i_end", c_int),
+                ("role", c_int), ("lane0", c_int), ("col0", c_int), ("scale", c_float), ("accumulate", c_int),
+                ("perm", c_int)]
+
+
+class WgradParams(Structure):
+    _fields_ = [("x", c_void_p), ("x_ctot", c_int), ("dy", c_void_p), ("dy_ctot", c_int),
+                ("batch", c_int), ("height", c_int), ("width", c_int),
+                ("nroles", c_int), ("roles", WgradRole * 4), ("ndst", c_int), ("dst", WgradDst * 16),
+                ("workspace", c_void_p)]
+
+
+class EdgeWgradParams(Structure):
+    _fields_ = [("s", c_void_p), ("gate", c_void_p), ("v", c_void_p), ("v_ctot", c_int), ("v_coff", c_int),
+                ("v2", c_void_p), ("v2_ctot", c_int), ("v2_coff", c_int), ("r", c_void_p), ("ssum", c_void_p),
+                ("batch", c_int), ("ns", c_int), ("height", c_int), ("width", c_int), ("channels", c_int)]
+
+
+EXTRA_STRUCTS = {"xmm_wgrad_role": WgradRole, "xmm_wgrad_dst": WgradDst, "xmm_wgrad_params": WgradParams,
+                 "xmm_edge_wgrad_params": EdgeWgradParams}
 
 # name -> (restype, argtypes); the non-GPU test-suite checks every name in include/xmm_b200.h is here
 # and exported by the shared object.
@@ -73,6 +102,10 @@ SIGNATURES = {
     "xmm_image_upsample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xmm_conv_first": (c_int, [POINTER(ConvFirstParams), c_void_p]),
     "xmm_conv_last": (c_int, [POINTER(ConvLastParams), c_void_p]),
+    "xmm_wgrad_workspace_bytes": (c_size_t, []),
+    "xmm_conv3x3_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
+    "xmm_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_float, c_int, c_void_p]),
+    "xmm_edge_wgrad": (c_int, [POINTER(EdgeWgradParams), c_void_p]),
 }
 
 _lib = None

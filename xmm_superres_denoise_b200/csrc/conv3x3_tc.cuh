@@ -51,7 +51,10 @@ struct ConvEpilogue {
   int r2_ctot, r2_coff;
   __nv_bfloat16* out;
   int out_ctot, out_coff;
-  int pixel_shuffle;  // 1: out is [B][2H][2W][out_ctot]; column group g=(i,j) -> pixel (2y+i,2x+j)
+  // 0: out is [B][H][W][out_ctot]
+  // 1: PixelShuffle(2) store: out is [B][2H][2W][out_ctot]; column group g=(i,j) -> pixel (2y+i,2x+j)
+  // 2: inverse (backward of 1): out is [B][H/2][W/2][out_ctot]; pixel (y,x) -> (y/2,x/2), channel block g=(y&1,x&1)
+  int pixel_shuffle;
 };
 
 struct ConvArgs {
@@ -88,6 +91,12 @@ struct ConvCfg {
     return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kBarBytes;
   }
 };
+
+__host__ __device__ __forceinline__ int shuffle_perm(int idx, int group) {
+  // packed index g*group + c  ->  PixelShuffle channel 4*c + g   (g = 2*i + j)
+  const int g = idx / group, c = idx - g * group;
+  return 4 * c + g;
+}
 
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
@@ -151,7 +160,11 @@ __device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const fl
     }
   }
   uint4* op;
-  if (e.pixel_shuffle) {
+  if (e.pixel_shuffle == 2) {
+    const int g = ((y & 1) << 1) | (x & 1);
+    const size_t lp = (size_t(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+    op = reinterpret_cast<uint4*>(e.out + lp * e.out_ctot + e.out_coff + g * NT + col0);
+  } else if (e.pixel_shuffle == 1) {
     constexpr int kGroup = NT / 4;  // channels of the shuffled (HR) tensor
     const int g = col0 / kGroup, c = col0 % kGroup;
     const size_t hp = (size_t(b) * (2 * H) + (2 * y + (g >> 1))) * (2 * W) + (2 * x + (g & 1));

@@ -126,6 +126,12 @@ struct ConvFirstArgs {
   __nv_bfloat16* out; int out_ctot, out_coff;
   __nv_bfloat16* out2; int out2_ctot, out2_coff;  // optional second copy (the trunk skip `fea`)
   int batch, cin, height, width;
+  // backward use (data gradient of conv_last): the input image is a gradient that only passes
+  // where the forward clamp did not saturate, and the result is multiplied by LeakyReLU'(act).
+  const float* gate;          // optional, same shape as `in`: v = (0 <= gate <= 1) ? in : 0
+  const __nv_bfloat16* mask;  // optional NHWC bf16 window: out *= (mask > 0 ? 1 : mask_slope)
+  int mask_ctot, mask_coff;
+  float mask_slope;
 };
 
 template <int F>
@@ -156,11 +162,27 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const ConvFirstArgs a) 
       for (int dx = 0; dx < 3; ++dx) {
         const int xx = x + dx - 1;
         float v = 0.0f;
-        if (yy >= 0 && yy < a.height && xx >= 0 && xx < a.width) v = __ldg(ip + size_t(yy) * a.width + xx);
+        if (yy >= 0 && yy < a.height && xx >= 0 && xx < a.width) {
+          v = __ldg(ip + size_t(yy) * a.width + xx);
+          if (a.gate != nullptr) {
+            const float gt = __ldg(a.gate + (size_t(b) * a.cin + c) * hw + size_t(yy) * a.width + xx);
+            if (!(gt >= 0.0f && gt <= 1.0f)) v = 0.0f;
+          }
+        }
         const float* wp = wsm + (c * 9 + dy * 3 + dx) * F;
 #pragma unroll
         for (int f = 0; f < F; ++f) acc[f] = fmaf(v, wp[f], acc[f]);
       }
+    }
+  }
+  if (a.mask != nullptr) {
+    const uint4* mp = reinterpret_cast<const uint4*>(a.mask + pix * a.mask_ctot + a.mask_coff);
+#pragma unroll
+    for (int q = 0; q < F / 8; ++q) {
+      float m[8];
+      unpack8(__ldg(mp + q), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[q * 8 + i] *= (m[i] > 0.0f ? 1.0f : a.mask_slope);
     }
   }
   uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ctot + a.out_coff);
@@ -227,6 +249,64 @@ __global__ void __launch_bounds__(128) conv_last_kernel(const ConvLastArgs a) {
     if (a.residual != nullptr) v += a.residual[oi];
     if (a.pre != nullptr) a.pre[oi] = v;
     a.out[oi] = a.clamp ? fminf(fmaxf(v, 0.0f), 1.0f) : v;
+  }
+}
+
+// ------------------------------------------------------------------------------ edge weight grads
+// R[o][c][tap] (+)= sum_p s[o][p] * (V[p + off(tap)][c] + V2[p + off(tap)][c]),   S[o] (+)= sum_p s[o][p]
+// with s an fp32 NCHW image (optionally gated by the forward clamp) and V a bf16 NHWC window.
+//   conv_last:  s = dL/d(out), V = its input features          -> dW[o][c][tap] = R, db[o] = S
+//   conv_first: s = the input image x, V = dL/d(fea)           -> dW[f][o][8-tap] = R[o][f][tap]
+// Block = C x 9 threads (one per (channel, tap)); each block walks a strip of pixels.
+struct EdgeWgradArgs {
+  const float* s;     // [B][ns][H][W]
+  const float* gate;  // optional clamp gate for s
+  const __nv_bfloat16* v; int v_ctot, v_coff;
+  const __nv_bfloat16* v2; int v2_ctot, v2_coff;  // optional second addend
+  float* r;           // [ns][C][9]
+  float* ssum;        // [ns] or nullptr
+  int batch, ns, height, width;
+  int pixels_per_block;
+};
+
+template <int C>
+__global__ void __launch_bounds__(C * 9) edge_wgrad_kernel(const EdgeWgradArgs a) {
+  const int c = threadIdx.x % C, tap = threadIdx.x / C;
+  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+  const size_t hw = size_t(a.height) * a.width;
+  const size_t npix = hw * a.batch;
+  const size_t p0 = size_t(blockIdx.x) * a.pixels_per_block;
+  const size_t p1 = p0 + a.pixels_per_block < npix ? p0 + a.pixels_per_block : npix;
+  const int b0 = int(p0 / hw);
+  const int rem0 = int(p0 - size_t(b0) * hw);
+  for (int o = 0; o < a.ns; ++o) {
+    float acc = 0.0f, ss = 0.0f;
+    int b = b0, y = rem0 / a.width, x = rem0 - (rem0 / a.width) * a.width;
+    for (size_t p = p0; p < p1; ++p) {
+      const size_t si = (size_t(b) * a.ns + o) * hw + size_t(y) * a.width + x;
+      float sv = __ldg(a.s + si);
+      if (a.gate != nullptr) {
+        const float gt = __ldg(a.gate + si);
+        if (!(gt >= 0.0f && gt <= 1.0f)) sv = 0.0f;
+      }
+      ss += sv;
+      const int yy = y + dy, xx = x + dx;
+      if (sv != 0.0f && yy >= 0 && yy < a.height && xx >= 0 && xx < a.width) {
+        const size_t q = (size_t(b) * a.height + yy) * a.width + xx;
+        float vv = __bfloat162float(a.v[q * a.v_ctot + a.v_coff + c]);
+        if (a.v2 != nullptr) vv += __bfloat162float(a.v2[q * a.v2_ctot + a.v2_coff + c]);
+        acc = fmaf(sv, vv, acc);
+      }
+      if (++x == a.width) {
+        x = 0;
+        if (++y == a.height) {
+          y = 0;
+          ++b;
+        }
+      }
+    }
+    atomicAdd(a.r + (size_t(o) * C + c) * 9 + tap, acc);
+    if (a.ssum != nullptr && threadIdx.x == 0) atomicAdd(a.ssum + o, ss);
   }
 }
 

@@ -13,12 +13,6 @@
 
 namespace xmm {
 
-__device__ __forceinline__ int shuffle_perm(int idx, int group) {
-  // packed index g*group + c  ->  PixelShuffle channel 4*c + g   (g = 2*i + j)
-  const int g = idx / group, c = idx - g * group;
-  return 4 * c + g;
-}
-
 __global__ void pack_jobs_kernel(const xmm_pack_job* __restrict__ jobs) {
   const xmm_pack_job& job = jobs[blockIdx.y];
   const int nblocks = job.nchunks * 9;

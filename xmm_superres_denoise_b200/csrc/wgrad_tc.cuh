@@ -1,0 +1,243 @@
+// Weight gradient of the 3x3 convolutions on the sm_100a tensor cores
+// (what autograd's cuDNN bwd-filter computes for rrdb_blocks.py:27-31 / generator_rrdb.py:39-45,93-101).
+//
+//   dW[tap][c][n] = sum over pixels p of  X[p + off(tap)][c] * dY[p][n]
+//
+// is a GEMM whose contraction dimension K is the PIXEL index, so both operands are "MN-major"
+// for the UMMA (channels are the contiguous dimension of NHWC): the A tile is the haloed
+// activation patch [pixels][64*xb channels], viewed once per tap exactly like the forward
+// kernel does, the B tile is the un-shifted dY patch [pixels][n channels].  One accumulator
+// D_tap[c][n] per tap lives in TMEM for the whole life of the persistent CTA (split-K over
+// pixel tiles), so a CTA can only own tap_count * n <= 512 columns: the launch is split into
+// ROLES (e.g. one role per filter row dy) and every role streams all pixel tiles.
+// At the end each CTA dumps its partial sums; wgrad_reduce_kernel adds them up per role and
+// scatters into the fp32 OIHW gradient tensors.
+//
+// Dense-block use (F = 32): X = the 5F-channel activation buffer, dY = the 5F-channel
+// gradient buffer (slot k-1 = dY_k).  Role "main(dy)": X channels 0..127 (x0..x3) against all
+// 160 dY columns, 3 taps -> 480 TMEM columns; role "tail": X channels 128..159 (x4) against
+// dY_5, 9 taps -> 288 columns.  Blocks (x_j, dY_k) with j >= k are computed but unused.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "conv3x3_tc.cuh"
+
+namespace xmm {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgStages = 2;
+constexpr int kWgBoxXBytes = 23552;   // 18*10 pixels * 128 B = 23040, padded to a 1024-B multiple
+constexpr int kWgBoxYBytes = 16384;   // 16*8 pixels * 128 B
+constexpr int kWgMaxRoles = 4;
+constexpr int kWgWsFloatsPerCta = 128 * 512;
+
+struct WgradRole {
+  int cta_begin, cta_count;
+  int tap_begin, tap_count;
+  int x_c0;      // first X channel of the M tile (box of 64 channels; beyond-ctot channels read as 0)
+  int x_boxes;   // 1 (M rows 64..127 alias rows 0..63) or 2
+  int y_c0;      // first dY channel of the N tile
+  int y_boxes;   // ceil(n / 64)
+  int n;         // N of the MMA (multiple of 16, <= 192)
+};
+
+struct WgradArgs {
+  WgradRole roles[kWgMaxRoles];
+  int nroles;
+  int batch, height, width;
+  int tiles_x, tiles_y, num_tiles;
+  float* ws;     // [gridDim.x][128 lanes][512 columns] fp32 partial sums
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
+                const WgradArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kWgStages], empty_bar[kWgStages], done_bar;
+  __shared__ uint32_t tmem_ptr_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // role lookup (uniform per CTA)
+  int ri = 0;
+  for (int r = 0; r < args.nroles; ++r)
+    if (int(blockIdx.x) >= args.roles[r].cta_begin && int(blockIdx.x) < args.roles[r].cta_begin + args.roles[r].cta_count) ri = r;
+  const WgradRole role = args.roles[ri];
+  const int stage_bytes = role.x_boxes * kWgBoxXBytes + role.y_boxes * kWgBoxYBytes;
+  const int first_tile = int(blockIdx.x) - role.cta_begin;
+  const bool has_work = first_tile < args.num_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_y);
+    for (int s = 0; s < kWgStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(&done_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(&tmem_ptr_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr_s;
+  const int tiles_per_img = args.tiles_x * args.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_tile; tile < args.num_tiles; tile += role.cta_count) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int ty = r / args.tiles_x;
+        const int tx = r - ty * args.tiles_x;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        ptx::mbar_expect_tx(&full_bar[stage], uint32_t(role.x_boxes * 18 * 10 * 128 + role.y_boxes * kWgBoxYBytes));
+        uint8_t* dst = smem + size_t(stage) * stage_bytes;
+        for (int xb = 0; xb < role.x_boxes; ++xb)
+          ptx::tma_load_4d(dst + xb * kWgBoxXBytes, &tmap_x, &full_bar[stage], role.x_c0 + 64 * xb, tx * kTileW - 1,
+                           ty * kTileH - 1, b);
+        uint8_t* ydst = dst + role.x_boxes * kWgBoxXBytes;
+        for (int yb = 0; yb < role.y_boxes; ++yb)
+          ptx::tma_load_4d(ydst + yb * kWgBoxYBytes, &tmap_y, &full_bar[stage], role.y_c0 + 64 * yb, tx * kTileW,
+                           ty * kTileH, b);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      const uint32_t idesc = ptx::umma_idesc_bf16_f32(128, role.n, 1, 1);
+      const uint32_t a_lbo = role.x_boxes > 1 ? uint32_t(kWgBoxXBytes) : 0u;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (int tile = first_tile; tile < args.num_tiles; tile += role.cta_count) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t x_addr = ptx::smem_u32(smem + size_t(stage) * stage_bytes);
+        const uint32_t y_addr = x_addr + uint32_t(role.x_boxes * kWgBoxXBytes);
+#pragma unroll 1
+        for (int s = 0; s < kTileH / 2; ++s) {  // 16 pixels (two tile rows) per MMA
+          const uint64_t bdesc = ptx::umma_smem_desc(y_addr + uint32_t(s * 2 * kTileW * 128), kWgBoxYBytes,
+                                                     kTileW * 128, ptx::UMMA_SW128);
+#pragma unroll 1
+          for (int t = 0; t < role.tap_count; ++t) {
+            const int tap = role.tap_begin + t;
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a_addr = x_addr + uint32_t(((2 * s + dy) * (kTileW + 2) + dx) * 128);
+            const uint64_t adesc = ptx::umma_smem_desc(a_addr, a_lbo, (kTileW + 2) * 128, ptx::UMMA_SW128);
+            ptx::umma_ss(tmem_base + uint32_t(t * role.n), adesc, bdesc, idesc, (first && s == 0) ? 0u : 1u);
+          }
+        }
+        first = false;
+        ptx::umma_commit(&empty_bar[stage]);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      ptx::umma_commit(&done_bar);
+    }
+  } else if (has_work) {
+    // epilogue: dump this CTA's accumulators  ws[cta][lane][col]
+    const int q = warp & 3;
+    ptx::mbar_wait(&done_bar, 0);
+    ptx::tc_fence_after();
+    const int cols = role.tap_count * role.n;
+    float* dst = args.ws + size_t(blockIdx.x) * kWgWsFloatsPerCta + size_t(q * 32 + lane) * 512;
+    for (int c0 = 0; c0 < cols; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<uint4*>(dst + c0 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// One destination tensor of the reduction: dW (fp32 OIHW [o_count][i_total][3][3]) gathers
+//   dW[o][i][tap] (+)= scale * sum over the role's CTAs of ws[cta][lane = i - x_c0][(tap - tap_begin) * n + y_col0 + o]
+// for i in [i_begin, i_end), from the role that owns (tap, i).
+struct WgradDst {
+  float* dw;
+  int o_count, i_total;
+  int i_begin, i_end;   // input channels taken from this role
+  int role;             // index into WgradArgs::roles (for taps in that role's range)
+  int lane0;            // ws lane of input channel i_begin
+  int col0;             // column (within one tap's n columns) of output channel 0
+  float scale;
+  int accumulate;       // 0: overwrite, 1: add to the existing gradient
+  int perm;             // 1: output channel o is the PixelShuffle-packed index (see shuffle_perm)
+};
+
+struct WgradReduceArgs {
+  WgradRole roles[kWgMaxRoles];
+  int nroles;
+  const float* ws;
+  int ndst;
+  WgradDst dst[16];
+};
+
+__global__ void wgrad_reduce_kernel(const WgradReduceArgs a, int num_tiles) {
+  const WgradDst d = a.dst[blockIdx.y];
+  const WgradRole role = a.roles[d.role];
+  const int ni = d.i_end - d.i_begin;
+  const int total = d.o_count * ni * role.tap_count;
+  int active = role.cta_count < num_tiles ? role.cta_count : num_tiles;  // CTAs beyond num_tiles wrote nothing
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int o = e % d.o_count;
+    const int rest = e / d.o_count;
+    const int i = rest % ni;
+    const int t = rest / ni;
+    const size_t off = size_t(d.lane0 + i) * 512 + size_t(t * role.n + d.col0 + o);
+    float s = 0.f;
+    for (int c = 0; c < active; ++c) s += a.ws[size_t(role.cta_begin + c) * kWgWsFloatsPerCta + off];
+    const int oo = d.perm ? shuffle_perm(o, d.o_count / 4) : o;
+    float* p = d.dw + (size_t(oo) * d.i_total + (d.i_begin + i)) * 9 + (role.tap_begin + t);
+    *p = d.accumulate ? (*p + d.scale * s) : d.scale * s;
+  }
+}
+
+// Column sums of a bf16 NHWC channel window: bias gradients  db[n] = scale * sum_p dY[p][c0 + n].
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ in, int ctot, int c0, int n, size_t npix,
+                              float* __restrict__ out, float scale) {
+  // blockDim.x = 256 threads: thread -> (pixel lane = tid / n8, channel group = tid % n8), n8 = n / 8
+  extern __shared__ float red[];
+  const int n8 = n / 8;
+  const int ppb = blockDim.x / n8;  // pixels per block iteration
+  const int cg = threadIdx.x % n8, pl = threadIdx.x / n8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pl < ppb) {
+    for (size_t p = size_t(blockIdx.x) * ppb + pl; p < npix; p += size_t(gridDim.x) * ppb) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + p * ctot + c0 + cg * 8)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  if (pl < ppb) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&red[cg * 8 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&out[i], scale * red[i]);
+}
+
+}  // namespace xmm

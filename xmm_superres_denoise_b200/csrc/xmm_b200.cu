@@ -7,6 +7,7 @@
 #include "edge_kernels.cuh"
 #include "host_common.cuh"
 #include "pack_weights.cuh"
+#include "wgrad_tc.cuh"
 
 #ifndef XMM_DEFAULT_TAP_MODE
 #define XMM_DEFAULT_TAP_MODE 0
@@ -151,13 +152,16 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   XMM_REQUIRE(p.cin > 0 && p.cin % p.kc == 0, "conv3x3: cin=%d is not a multiple of kc=%d", p.cin, p.kc);
   XMM_REQUIRE(p.in_ctot % 8 == 0 && p.in_coff % 8 == 0 && p.in_coff + p.cin <= p.in_ctot,
               "conv3x3: input channel window [%d,%d) of %d", p.in_coff, p.in_coff + p.cin, p.in_ctot);
-  const int out_c = p.pixel_shuffle ? p.cout / 4 : p.cout;
+  const int out_c = p.pixel_shuffle == 1 ? p.cout / 4 : (p.pixel_shuffle == 2 ? 4 * p.cout : p.cout);
+  XMM_REQUIRE(p.pixel_shuffle >= 0 && p.pixel_shuffle <= 2, "conv3x3: pixel_shuffle must be 0, 1 or 2");
+  XMM_REQUIRE(p.pixel_shuffle != 2 || (p.height % 2 == 0 && p.width % 2 == 0 && !p.r1 && !p.r2),
+              "conv3x3: inverse pixel shuffle needs even height/width and no residual");
   XMM_REQUIRE(p.out_ctot % 8 == 0 && p.out_coff % 8 == 0 && p.out_coff + out_c <= p.out_ctot,
               "conv3x3: output channel window [%d,%d) of %d", p.out_coff, p.out_coff + out_c, p.out_ctot);
   XMM_REQUIRE(!p.mask || (p.mask_ctot % 8 == 0 && p.mask_coff % 8 == 0), "conv3x3: mask window alignment");
   XMM_REQUIRE(!p.r1 || (p.r1_ctot % 8 == 0 && p.r1_coff % 8 == 0), "conv3x3: r1 window alignment");
   XMM_REQUIRE(!p.r2 || (p.r2_ctot % 8 == 0 && p.r2_coff % 8 == 0), "conv3x3: r2 window alignment");
-  XMM_REQUIRE(!p.pixel_shuffle || (!p.mask && !p.r1 && !p.r2 && p.cout % 128 == 0),
+  XMM_REQUIRE(p.pixel_shuffle != 1 || (!p.mask && !p.r1 && !p.r2 && p.cout % 128 == 0),
               "conv3x3: pixel_shuffle needs cout %% 128 == 0 and no mask/residual");
   XMM_REQUIRE((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(p.wblob) & 15) == 0,
@@ -254,6 +258,10 @@ extern "C" int xmm_conv_first(const xmm_conv_first_params* pp, void* stream) {
   a.out = static_cast<__nv_bfloat16*>(p.out); a.out_ctot = p.out_ctot; a.out_coff = p.out_coff;
   a.out2 = static_cast<__nv_bfloat16*>(p.out2); a.out2_ctot = p.out2_ctot; a.out2_coff = p.out2_coff;
   a.batch = p.batch; a.cin = p.cin; a.height = p.height; a.width = p.width;
+  a.gate = p.gate;
+  a.mask = static_cast<const __nv_bfloat16*>(p.mask); a.mask_ctot = p.mask_ctot; a.mask_coff = p.mask_coff;
+  a.mask_slope = p.mask_slope;
+  XMM_REQUIRE(!p.mask || (p.mask_ctot % 8 == 0 && p.mask_coff % 8 == 0), "conv_first: mask window alignment");
   const size_t npix = size_t(p.batch) * p.height * p.width;
   const unsigned grid = unsigned((npix + 127) / 128);
   const size_t smem = (size_t(p.cin) * 9 + 1) * p.filters * sizeof(float);
@@ -287,6 +295,148 @@ extern "C" int xmm_conv_last(const xmm_conv_last_params* pp, void* stream) {
   if (p.filters == 32) conv_last_kernel<32><<<grid, 128, smem, s>>>(a);
   else if (p.filters == 64) conv_last_kernel<64><<<grid, 128, smem, s>>>(a);
   else return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv_last: filters=%d (supported: 32, 64)", p.filters);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+// ----------------------------------------------------------------------------- weight gradients
+extern "C" size_t xmm_wgrad_workspace_bytes(void) {
+  DeviceInfo d;
+  int sms = 160;
+  if (device_info(&d) == XMM_OK && d.sm_count > 0) sms = d.sm_count;
+  return size_t(sms) * kWgWsFloatsPerCta * sizeof(float);
+}
+
+extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "wgrad: null params");
+  const xmm_wgrad_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.x && p.dy && p.workspace, "wgrad: null tensor pointer");
+  XMM_REQUIRE(p.batch > 0 && p.height > 0 && p.width > 0, "wgrad: bad shape");
+  XMM_REQUIRE(p.x_ctot % 8 == 0 && p.dy_ctot % 8 == 0, "wgrad: channel counts must be multiples of 8");
+  XMM_REQUIRE(p.nroles >= 1 && p.nroles <= kWgMaxRoles && p.ndst >= 1 && p.ndst <= 16, "wgrad: %d roles / %d dsts",
+              p.nroles, p.ndst);
+  XMM_REQUIRE(dev.sm_count >= p.nroles, "wgrad: fewer SMs than roles");
+  WgradArgs a{};
+  WgradReduceArgs ra{};
+  a.nroles = ra.nroles = p.nroles;
+  double cost[kWgMaxRoles], total = 0;
+  size_t max_stage = 0;
+  for (int r = 0; r < p.nroles; ++r) {
+    const xmm_wgrad_role& q = p.roles[r];
+    XMM_REQUIRE(q.tap_begin >= 0 && q.tap_count >= 1 && q.tap_begin + q.tap_count <= 9, "wgrad: role %d taps", r);
+    XMM_REQUIRE(q.n >= 16 && q.n % 16 == 0 && q.n <= 192 && q.tap_count * q.n <= 512,
+                "wgrad: role %d needs %d x %d TMEM columns (max 512)", r, q.tap_count, q.n);
+    XMM_REQUIRE((q.x_boxes == 1 || q.x_boxes == 2) && q.x_c0 % 8 == 0 && q.y_c0 % 8 == 0 && q.x_c0 < p.x_ctot &&
+                    q.y_c0 + q.n <= ((p.dy_ctot + 63) / 64) * 64 + 64,
+                "wgrad: role %d channel windows", r);
+    WgradRole& w = a.roles[r];
+    w.tap_begin = q.tap_begin; w.tap_count = q.tap_count; w.x_c0 = q.x_c0; w.x_boxes = q.x_boxes;
+    w.y_c0 = q.y_c0; w.n = q.n; w.y_boxes = (q.n + 63) / 64;
+    const double per_mma = q.n / 2.0 > 47.0 ? q.n / 2.0 : 47.0;  // measured tcgen05 floor, profiles/r01_probe1
+    cost[r] = q.tap_count * per_mma;
+    total += cost[r];
+    const size_t st = size_t(w.x_boxes) * kWgBoxXBytes + size_t(w.y_boxes) * kWgBoxYBytes;
+    if (st > max_stage) max_stage = st;
+  }
+  int assigned = 0;
+  for (int r = 0; r < p.nroles; ++r) {
+    int c = int(dev.sm_count * cost[r] / total);
+    if (c < 1) c = 1;
+    a.roles[r].cta_count = c;
+    assigned += c;
+  }
+  for (int r = 0; assigned != dev.sm_count; r = (r + 1) % p.nroles) {  // distribute the rounding remainder
+    if (assigned < dev.sm_count) { ++a.roles[r].cta_count; ++assigned; }
+    else if (a.roles[r].cta_count > 1) { --a.roles[r].cta_count; --assigned; }
+  }
+  int begin = 0;
+  for (int r = 0; r < p.nroles; ++r) {
+    a.roles[r].cta_begin = begin;
+    begin += a.roles[r].cta_count;
+    ra.roles[r] = a.roles[r];
+  }
+  a.batch = p.batch; a.height = p.height; a.width = p.width;
+  a.tiles_x = (p.width + kTileW - 1) / kTileW;
+  a.tiles_y = (p.height + kTileH - 1) / kTileH;
+  a.num_tiles = a.tiles_x * a.tiles_y * p.batch;
+  a.ws = p.workspace;
+  const size_t smem = 1024 + kWgStages * max_stage;
+  XMM_REQUIRE(smem <= size_t(dev.max_smem_optin - 1024), "wgrad: stage of %zu B does not fit twice in shared memory", max_stage);
+
+  ra.ws = p.workspace;
+  ra.ndst = p.ndst;
+  for (int i = 0; i < p.ndst; ++i) {
+    const xmm_wgrad_dst& q = p.dst[i];
+    XMM_REQUIRE(q.dw && q.role >= 0 && q.role < p.nroles && q.i_begin >= 0 && q.i_end > q.i_begin &&
+                    q.i_end <= q.i_total && q.lane0 >= 0 && q.lane0 + (q.i_end - q.i_begin) <= 128 && q.col0 >= 0 &&
+                    q.col0 + q.o_count <= p.roles[q.role].n,
+                "wgrad: destination %d is inconsistent with its role", i);
+    WgradDst& d = ra.dst[i];
+    d.dw = q.dw; d.o_count = q.o_count; d.i_total = q.i_total; d.i_begin = q.i_begin; d.i_end = q.i_end;
+    d.role = q.role; d.lane0 = q.lane0; d.col0 = q.col0; d.scale = q.scale; d.accumulate = q.accumulate; d.perm = q.perm;
+  }
+
+  CUtensorMap tx, ty;
+  rc = cached_tmap(&tx, p.x, p.batch, p.height, p.width, p.x_ctot, 64, kTileW + 2, kHaloH);
+  if (rc != XMM_OK) return rc;
+  rc = cached_tmap(&ty, p.dy, p.batch, p.height, p.width, p.dy_ctot, 64, kTileW, kTileH);
+  if (rc != XMM_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XMM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dev.max_smem_optin - 1024));  // the kernel also has static shared memory
+    attr_set = true;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  wgrad_tc_kernel<<<dev.sm_count, kWgThreads, smem, s>>>(tx, ty, a);
+  XMM_CUDA_OK(cudaGetLastError());
+  wgrad_reduce_kernel<<<dim3(24, p.ndst), 256, 0, s>>>(ra, a.num_tiles);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_colsum_bf16(const void* in, int ctot, int c0, int n, size_t npix, float* out, float scale,
+                               int accumulate, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(in && out, "colsum: null tensor pointer");
+  XMM_REQUIRE(n > 0 && n % 8 == 0 && n <= 256 && c0 % 8 == 0 && ctot % 8 == 0 && c0 + n <= ctot,
+              "colsum: channel window [%d,%d) of %d", c0, c0 + n, ctot);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!accumulate) XMM_CUDA_OK(cudaMemsetAsync(out, 0, size_t(n) * sizeof(float), s));
+  if (npix == 0) return XMM_OK;
+  colsum_kernel<<<dev.sm_count * 8, 256, size_t(n) * sizeof(float), s>>>(static_cast<const __nv_bfloat16*>(in), ctot,
+                                                                        c0, n, npix, out, scale);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_edge_wgrad(const xmm_edge_wgrad_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "edge_wgrad: null params");
+  const xmm_edge_wgrad_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.s && p.v && p.r, "edge_wgrad: null tensor pointer");
+  XMM_REQUIRE(p.ns >= 1 && p.ns <= 4 && p.batch > 0 && p.height > 0 && p.width > 0, "edge_wgrad: bad shape");
+  EdgeWgradArgs a{};
+  a.s = p.s; a.gate = p.gate;
+  a.v = static_cast<const __nv_bfloat16*>(p.v); a.v_ctot = p.v_ctot; a.v_coff = p.v_coff;
+  a.v2 = static_cast<const __nv_bfloat16*>(p.v2); a.v2_ctot = p.v2_ctot; a.v2_coff = p.v2_coff;
+  a.r = p.r; a.ssum = p.ssum; a.batch = p.batch; a.ns = p.ns; a.height = p.height; a.width = p.width;
+  const size_t npix = size_t(p.batch) * p.height * p.width;
+  int ppb = int((npix + size_t(dev.sm_count) * 16 - 1) / (size_t(dev.sm_count) * 16));
+  if (ppb < 64) ppb = 64;
+  a.pixels_per_block = ppb;
+  const unsigned grid = unsigned((npix + ppb - 1) / ppb);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.channels == 32) edge_wgrad_kernel<32><<<grid, 32 * 9, 0, s>>>(a);
+  else if (p.channels == 64) edge_wgrad_kernel<64><<<grid, 64 * 9, 0, s>>>(a);
+  else return fail(XMM_ERR_UNSUPPORTED_SHAPE, "edge_wgrad: channels=%d (supported: 32, 64)", p.channels);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }

@@ -111,7 +111,7 @@ class WeightArena:
             self._versions = None
         versions = tuple(p._version for p in params)
         if versions != self._versions:
-            _lib.check(_lib.load().xmm_pack_weights(self._jobs_dev.data_ptr(), len(self._order), _lib.stream_ptr()))
+            ops.pack_weights(self._jobs_dev.data_ptr(), len(self._order))
             self._versions = versions
 
 
@@ -240,7 +240,7 @@ class RRDBEngine:
         cur = bufs["trunk"]
         for s in range(self.num_upsample):
             ops.conv3x3(cur, 0, self.nf, self.arena.ptr(f"f.up{s}"), self.kc, 4 * self.nf, bufs[f"up{s}"], 0,
-                        lrelu=0.01, pixel_shuffle=True)
+                        lrelu=0.01, pixel_shuffle=1)
             cur = bufs[f"up{s}"]
         ops.conv3x3(cur, 0, self.nf, self.arena.ptr("f.hr"), self.kc, self.nf, bufs["hr"], 0, lrelu=0.2)
         hh, ww = cur.shape[1], cur.shape[2]

@@ -11,7 +11,16 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import Conv3x3Params, ConvFirstParams, ConvLastParams, NormalizeParams
+from ._lib import (Conv3x3Params, ConvFirstParams, ConvLastParams, EdgeWgradParams, NormalizeParams, WgradDst,
+                   WgradParams, WgradRole)
+
+
+LAUNCHES = 0  # kernels launched through this module since the caller last reset it (bench.py's gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -29,7 +38,7 @@ def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, 
             r1: Optional[torch.Tensor] = None, r1_coff: int = 0, s1: float = 0.0,
             r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
             mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
-            pixel_shuffle: bool = False, tap_mode: int = 0) -> None:
+            pixel_shuffle: int = 0, tap_mode: int = 0) -> None:
     """out[..., out_coff:out_coff+cout] = epilogue(conv3x3(inp[..., in_coff:in_coff+cin])).
 
     See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
@@ -54,17 +63,21 @@ def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, 
         _nhwc(r2, "conv3x3 r2")
         p.r2, p.r2_ctot, p.r2_coff = r2.data_ptr(), r2.shape[3], r2_coff
     p.s2 = s2
-    exp = (b, 2 * h, 2 * w) if pixel_shuffle else (b, h, w)
+    pixel_shuffle = int(pixel_shuffle)
+    exp = {0: (b, h, w), 1: (b, 2 * h, 2 * w), 2: (b, h // 2, w // 2)}[pixel_shuffle]
     if tuple(out.shape[:3]) != exp:
         raise RuntimeError(f"conv3x3 output: expected spatial shape {exp}, got {tuple(out.shape[:3])}")
     p.out, p.out_ctot, p.out_coff = out.data_ptr(), out.shape[3], out_coff
-    p.pixel_shuffle = 1 if pixel_shuffle else 0
+    p.pixel_shuffle = pixel_shuffle
     p.tap_mode = tap_mode
     _lib.check(_lib.load().xmm_conv3x3_bf16(ctypes.byref(p), _lib.stream_ptr()))
+    _count()
 
 
 def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
-               out_coff: int, out2: Optional[torch.Tensor] = None, out2_coff: int = 0) -> None:
+               out_coff: int, out2: Optional[torch.Tensor] = None, out2_coff: int = 0, *,
+               gate: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, mask_coff: int = 0,
+               mask_slope: float = 1.0) -> None:
     """fp32 NCHW image -> bf16 NHWC features (generator_rrdb.py:31-37,67)."""
     _lib.require_cuda_tensor(x, torch.float32, "conv_first input")
     _lib.require_cuda_tensor(weight, torch.float32, "conv_first weight")
@@ -77,7 +90,17 @@ def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     if out2 is not None:
         _nhwc(out2, "conv_first output2")
         p.out2, p.out2_ctot, p.out2_coff = out2.data_ptr(), out2.shape[3], out2_coff
+    if gate is not None:
+        _lib.require_cuda_tensor(gate, torch.float32, "conv_first gate")
+        if gate.shape != x.shape:
+            raise RuntimeError("conv_first gate: shape must equal the input shape")
+        p.gate = gate.data_ptr()
+    if mask is not None:
+        _nhwc(mask, "conv_first mask")
+        p.mask, p.mask_ctot, p.mask_coff = mask.data_ptr(), mask.shape[3], mask_coff
+    p.mask_slope = mask_slope
     _lib.check(_lib.load().xmm_conv_first(ctypes.byref(p), _lib.stream_ptr()))
+    _count()
 
 
 def conv_last(inp: torch.Tensor, in_coff: int, weight: torch.Tensor, bias: Optional[torch.Tensor],
@@ -103,6 +126,7 @@ def conv_last(inp: torch.Tensor, in_coff: int, weight: torch.Tensor, bias: Optio
     p.batch, p.cout, p.height, p.width, p.filters = b, weight.shape[0], h, w, weight.shape[1]
     p.clamp = 1 if clamp else 0
     _lib.check(_lib.load().xmm_conv_last(ctypes.byref(p), _lib.stream_ptr()))
+    _count()
 
 
 def normalize(inp: torch.Tensor, max_val: float, stretch_mode: str, *, out: Optional[torch.Tensor] = None,
@@ -127,6 +151,7 @@ def normalize(inp: torch.Tensor, max_val: float, stretch_mode: str, *, out: Opti
         scratch = torch.zeros(1, dtype=torch.float32, device=inp.device)
         p.scratch = scratch.data_ptr()
     _lib.check(_lib.load().xmm_normalize(ctypes.byref(p), _lib.stream_ptr()))
+    _count(1 if max_val > 0 else 2)
     return out
 
 
@@ -139,6 +164,7 @@ def denormalize(inp: torch.Tensor, max_vals: torch.Tensor, stretch_mode: str) ->
     per_image = inp.numel() // inp.shape[0] if inp.dim() > 0 and inp.shape[0] > 0 else inp.numel()
     _lib.check(_lib.load().xmm_denormalize(inp.data_ptr(), out.data_ptr(), inp.numel(), per_image, mv.data_ptr(),
                                            mv.numel(), _lib.STRETCH_MODES[stretch_mode], _lib.stream_ptr()))
+    _count()
     return out
 
 
@@ -149,4 +175,76 @@ def image_upsample(x: torch.Tensor, scale: int) -> torch.Tensor:
     n_img = x.numel() // (h * w) if h * w else 0
     out = torch.empty(*x.shape[:-2], h * scale, w * scale, dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().xmm_image_upsample(x.data_ptr(), out.data_ptr(), n_img, h, w, scale, _lib.stream_ptr()))
+    _count()
     return out
+
+
+def pack_weights(jobs_dev_ptr: int, njobs: int) -> None:
+    """Repack every layer listed in the device-side job table (one launch)."""
+    _lib.check(_lib.load().xmm_pack_weights(jobs_dev_ptr, njobs, _lib.stream_ptr()))
+    _count()
+
+
+_WS = {}
+
+
+def wgrad_workspace(device: torch.device) -> torch.Tensor:
+    ws = _WS.get(str(device))
+    if ws is None:
+        ws = torch.empty(_lib.load().xmm_wgrad_workspace_bytes() // 4, dtype=torch.float32, device=device)
+        _WS[str(device)] = ws
+    return ws
+
+
+def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, roles, dsts) -> None:
+    """Tensor-core weight gradient.  roles: [(tap_begin, tap_count, x_c0, x_boxes, y_c0, n)];
+    dsts: [(dw, o_count, i_total, i_begin, i_end, role, lane0, col0, scale, accumulate, perm)]."""
+    _nhwc(x, "wgrad x")
+    _nhwc(dy, "wgrad dy")
+    if x.shape[:3] != dy.shape[:3]:
+        raise RuntimeError("wgrad: x and dy must have the same batch / spatial shape")
+    p = WgradParams()
+    p.x, p.x_ctot, p.dy, p.dy_ctot = x.data_ptr(), x.shape[3], dy.data_ptr(), dy.shape[3]
+    p.batch, p.height, p.width = x.shape[0], x.shape[1], x.shape[2]
+    p.nroles = len(roles)
+    for dst, r in zip(p.roles, roles):
+        dst.tap_begin, dst.tap_count, dst.x_c0, dst.x_boxes, dst.y_c0, dst.n = r
+    p.ndst = len(dsts)
+    for dst, d in zip(p.dst, dsts):
+        dw = d[0]
+        _lib.require_cuda_tensor(dw, torch.float32, "wgrad dw")
+        (dst.o_count, dst.i_total, dst.i_begin, dst.i_end, dst.role, dst.lane0, dst.col0, dst.scale, dst.accumulate,
+         dst.perm) = d[1:]
+        dst.dw = dw.data_ptr()
+    p.workspace = wgrad_workspace(x.device).data_ptr()
+    _lib.check(_lib.load().xmm_conv3x3_wgrad(ctypes.byref(p), _lib.stream_ptr()))
+    _count(2)
+
+
+def colsum(inp: torch.Tensor, c0: int, n: int, out: torch.Tensor, scale: float = 1.0, accumulate: bool = False) -> None:
+    """out[i] (+)= scale * sum over pixels of inp[..., c0 + i]  (bias gradient)."""
+    _nhwc(inp, "colsum input")
+    _lib.require_cuda_tensor(out, torch.float32, "colsum output")
+    npix = inp.shape[0] * inp.shape[1] * inp.shape[2]
+    _lib.check(_lib.load().xmm_colsum_bf16(inp.data_ptr(), inp.shape[3], c0, n, npix, out.data_ptr(), scale,
+                                           int(accumulate), _lib.stream_ptr()))
+    _count()
+
+
+def edge_wgrad(s: torch.Tensor, v: torch.Tensor, v_coff: int, channels: int, r: torch.Tensor,
+               ssum: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+               v2: Optional[torch.Tensor] = None, v2_coff: int = 0) -> None:
+    """r[o][c][tap] += sum_p s[o][p] * (v + v2)[p + off(tap)][c];  ssum[o] += sum_p s[o][p]."""
+    _lib.require_cuda_tensor(s, torch.float32, "edge_wgrad s")
+    _nhwc(v, "edge_wgrad v")
+    _lib.require_cuda_tensor(r, torch.float32, "edge_wgrad r")
+    p = EdgeWgradParams()
+    p.s, p.gate = s.data_ptr(), _ptr(gate)
+    p.v, p.v_ctot, p.v_coff = v.data_ptr(), v.shape[3], v_coff
+    if v2 is not None:
+        _nhwc(v2, "edge_wgrad v2")
+        p.v2, p.v2_ctot, p.v2_coff = v2.data_ptr(), v2.shape[3], v2_coff
+    p.r, p.ssum = r.data_ptr(), _ptr(ssum)
+    p.batch, p.ns, p.height, p.width, p.channels = s.shape[0], s.shape[1], s.shape[2], s.shape[3], channels
+    _lib.check(_lib.load().xmm_edge_wgrad(ctypes.byref(p), _lib.stream_ptr()))
+    _count()
