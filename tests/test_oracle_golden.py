@@ -9,7 +9,7 @@ import torch
 
 from oracle import ref_loader
 from oracle import rrdb_oracle as O
-from oracle.make_golden import LR_MAX, counts_like_input, det_input
+from oracle.make_golden import LR_MAX, counts_like_input, det_input, probe_like
 from oracle.synthetic import pad_to
 
 from helpers import load_case, rel_l2
@@ -26,7 +26,7 @@ def test_network_forward_backward_matches_reference_golden(golden_dir, name):
     out = O.model_forward(x, sd, kind, 1)
     assert out.shape == g["out"].shape
     np.testing.assert_allclose(out.detach().numpy(), g["out"], rtol=0, atol=2e-6)
-    probe = det_input(tuple(out.shape), seed + 29) - 0.5
+    probe = probe_like(tuple(out.shape), seed + 29)
     (out * probe).sum().backward()
     assert rel_l2(x.grad, g["grad_x"]) < 1e-5
     for key in g.files:

@@ -1,0 +1,255 @@
+"""Training half of the engine: forward with saved activations + the hand-scheduled backward.
+
+What autograd + cuDNN do for the reference (conv bwd-data, conv bwd-filter, LeakyReLU / clamp /
+pixel-shuffle / residual backward, rrdb_blocks.py:37-70, generator_rrdb.py:66-137) is here an
+explicit launch sequence over the same two tensor-core kernels:
+
+* data gradients reuse ``conv3x3`` (the gradient of a correlation is a correlation with the
+  flipped, transposed filter).  For a dense block the gradient of x_j is ONE convolution over
+  the already-complete gradient slots dY_{j+1..5} -- they are adjacent channels of the block's
+  gradient buffer, mirroring how the forward reads x_0..x_{k-1} -- with LeakyReLU' taken from
+  the stored activation (in-place LeakyReLU keeps only the output; slope > 0 makes sign(out)
+  exact) fused in the epilogue, and the block / RRDB skip connections as scaled residual terms;
+* weight gradients use ``conv3x3_wgrad`` once per dense block (all five layers at once).
+
+Buffers per dense block: activations A = [x0|x1|x2|x3|x4] (kept from the forward), gradients
+G = [dY1|dY2|dY3|dY4|g] where g = dL/d(block output) (conv5's 0.2 is folded into the packed
+weights).  Three G buffers rotate: RDB3 -> ring[2], RDB2 -> ring[1], RDB1 -> ring[0].
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import RRDBEngine, _Blob, _Segment
+
+
+def _dgrad_blob(name: str, convs, j: int, f: int, kc: int, conv5_scale: float) -> _Blob:
+    """Gradient of x_j of a dense block: K runs over dY_{j+1}..dY_5 (F channels each)."""
+    segs = []
+    for k in range(j + 1, 6):
+        w = convs[k - 1].weight
+        segs.append(_Segment(w, w.shape[1], 0, j * f, 1, (k - j - 1) * f, f, conv5_scale if k == 5 else 1.0))
+    return _Blob(name, f, kc, (5 - j) * f // kc, segs, None)
+
+
+def _transpose_blob(name: str, conv, kc: int, perm: int = 0) -> _Blob:
+    """Data gradient of a plain conv: rows = its input channels, K = its output channels."""
+    cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+    return _Blob(name, cin, kc, cout // kc, [_Segment(conv.weight, cin, 0, 0, 1, 0, cout, 1.0)], None, perm)
+
+
+class TrainEngine(RRDBEngine):
+    def __init__(self, gen, kind: str) -> None:
+        super().__init__(gen, kind)
+        if self.nf != 32:
+            raise NotImplementedError(
+                f"training with num_filters={self.nf}: the weight-gradient role table is built for 32 filters")
+        f, kc = self.nf, self.kc
+        for i, rrdb in enumerate(gen.rrdb):
+            for r, rdb in enumerate((rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)):
+                convs = [getattr(rdb, f"conv{k}") for k in range(1, 6)]
+                for j in range(5):
+                    self.arena.add(_dgrad_blob(f"d.{i}.{r}.{j}", convs, j, f, kc, 0.04 if r == 2 else 0.2))
+        self.arena.add(_transpose_blob("d.trunk", gen.trunk_conv, kc))
+        if kind == "sr":
+            for s in range(self.num_upsample):
+                self.arena.add(_transpose_blob(f"d.up{s}", gen.upsampling[3 * s], kc, perm=1))
+            self.arena.add(_transpose_blob("d.hr", gen.HRconv, kc))
+        self.generation = 0
+        self._params = list(gen.parameters())
+        self._pindex = {id(p): n for n, p in enumerate(self._params)}
+
+    # ------------------------------------------------------------------ buffers
+    def _train_buffers(self, b: int, h: int, w: int, device: torch.device) -> Dict[str, object]:
+        key = ("train", b, h, w, str(device))
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            self._bufs.clear()
+            f = self.nf
+            bf = dict(dtype=torch.bfloat16, device=device)
+            nrdb = 3 * self.nb
+            act = [torch.empty(b, h, w, 5 * f, **bf) for _ in range(nrdb)]
+            act.append(torch.empty(b, h, w, f, **bf))  # output of the last RRDB
+            bufs = {"act": act, "trunk": torch.empty(b, h, w, f, **bf),
+                    "ring": [torch.empty(b, h, w, 5 * f, **bf) for _ in range(3)],
+                    "d_trunk": torch.empty(b, h, w, f, **bf), "d_fea": torch.empty(b, h, w, f, **bf)}
+            hh, ww = h, w
+            if self.kind == "sr":
+                for s in range(self.num_upsample):
+                    hh, ww = 2 * hh, 2 * ww
+                    bufs[f"up{s}"] = torch.empty(b, hh, ww, f, **bf)
+                    bufs[f"d_up{s}"] = torch.empty(b, hh // 2, ww // 2, 4 * f, **bf)  # un-shuffled gradient
+                bufs["hr"] = torch.empty(b, hh, ww, f, **bf)
+                bufs["d_hr"] = torch.empty(b, hh, ww, f, **bf)
+            bufs["pre"] = torch.empty(b, self.gen.out_channels, hh, ww, dtype=torch.float32, device=device)
+            self._bufs[key] = bufs
+        return bufs
+
+    # ------------------------------------------------------------------ forward
+    def forward_train(self, x: torch.Tensor):
+        self._check_input(x)
+        g = self.gen
+        x = x.contiguous().float()
+        b, _, h, w = x.shape
+        self.arena.ensure(x.device)
+        bufs = self._train_buffers(b, h, w, x.device)
+        self.generation += 1
+        self._trunk_forward(x, bufs["act"], bufs["act"][0], bufs["trunk"])
+        if self.kind == "dn":
+            if g.in_channels != g.out_channels:
+                raise RuntimeError("GeneratorRRDB_DN adds its input to its output: in_channels must equal out_channels")
+            out = torch.empty(b, g.out_channels, h, w, dtype=torch.float32, device=x.device)
+            ops.conv_last(bufs["trunk"], 0, g.conv_last.weight, g.conv_last.bias, out, residual=x, pre=bufs["pre"])
+            return out, bufs
+        cur = bufs["trunk"]
+        for s in range(self.num_upsample):
+            ops.conv3x3(cur, 0, self.nf, self.arena.ptr(f"f.up{s}"), self.kc, 4 * self.nf, bufs[f"up{s}"], 0,
+                        lrelu=0.01, pixel_shuffle=1)
+            cur = bufs[f"up{s}"]
+        ops.conv3x3(cur, 0, self.nf, self.arena.ptr("f.hr"), self.kc, self.nf, bufs["hr"], 0, lrelu=0.2)
+        out = torch.empty(b, g.out_channels, cur.shape[1], cur.shape[2], dtype=torch.float32, device=x.device)
+        ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, pre=bufs["pre"])
+        return out, bufs
+
+    # ------------------------------------------------------------------ backward
+    def _grad_views(self, device: torch.device) -> List[torch.Tensor]:
+        """Fresh flat fp32 gradient buffer (autograd may adopt the returned tensors as .grad)."""
+        total = sum(p.numel() for p in self._params)
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        views, off = [], 0
+        for p in self._params:
+            views.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.last_flat_grad = flat
+        return views
+
+    def _gv(self, grads, p: torch.Tensor) -> torch.Tensor:
+        return grads[self._pindex[id(p)]]
+
+    def _single_conv_wgrad(self, conv, x: torch.Tensor, dy: torch.Tensor, grads, perm: int = 0) -> None:
+        f = self.nf
+        n = conv.weight.shape[0]
+        dw = self._gv(grads, conv.weight)
+        if n == f:
+            ops.conv3x3_wgrad(x, dy, [(0, 9, 0, 1, 0, f)], [(dw, n, f, 0, f, 0, 0, 0, 1.0, 0, perm)])
+        else:  # F -> 4F: one role per filter row (3 taps x 128 columns of TMEM)
+            ops.conv3x3_wgrad(x, dy, [(3 * d, 3, 0, 1, 0, n) for d in range(3)],
+                              [(dw, n, f, 0, f, d, 0, 0, 1.0, 0, perm) for d in range(3)])
+        if conv.bias is not None:
+            db = self._gv(grads, conv.bias)
+            if perm:
+                tmp = torch.empty(n, dtype=torch.float32, device=dy.device)
+                ops.colsum(dy, 0, n, tmp)
+                db.copy_(tmp.view(4, n // 4).t().reshape(n))  # packed g*F+c -> channel 4c+g
+            else:
+                ops.colsum(dy, 0, n, db)
+
+    def _rdb_backward(self, i: int, r: int, bufs, grads, d_fea: torch.Tensor) -> None:
+        f, kc, a = self.nf, self.kc, self.arena
+        act, ring = bufs["act"], bufs["ring"]
+        A, G = act[3 * i + r], ring[r]
+        for j in range(4, 0, -1):  # dY_j = LeakyReLU'(x_j) * sum_k dgrad_k(dY_k)
+            ops.conv3x3(G, j * f, (5 - j) * f, a.ptr(f"d.{i}.{r}.{j}"), kc, f, G, (j - 1) * f, mask=A,
+                        mask_coff=j * f, mask_slope=0.2)
+        # gradient of the block input: + skip connection(s)
+        if r == 2:    # out_rrdb = 0.2 * out_rdb3 + x_rrdb ; G[4] holds E_i = dL/d(out_rrdb)
+            ops.conv3x3(G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[1], 4 * f, r1=G, r1_coff=4 * f, s1=0.2)
+        elif r == 1:
+            ops.conv3x3(G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[0], 4 * f, r1=G, r1_coff=4 * f, s1=1.0)
+        else:         # RDB1: + g_1 + E_i (RRDB skip); result is E_{i-1}, or dL/d(fea) through the trunk for i == 0
+            out, ocoff = (ring[2], 4 * f) if i > 0 else (d_fea, 0)
+            ops.conv3x3(G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, out, ocoff, r1=G, r1_coff=4 * f, s1=1.0,
+                        r2=ring[2], r2_coff=4 * f, s2=1.0)
+
+    def _rdb_wgrad(self, i: int, r: int, bufs, grads) -> None:
+        f = self.nf
+        rrdb = self.gen.rrdb[i]
+        rdb = (rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)[r]
+        A, G = bufs["act"][3 * i + r], bufs["ring"][r]
+        s5 = 0.04 if r == 2 else 0.2
+        roles = [(3 * d, 3, 0, 2, 0, 5 * f) for d in range(3)] + [(0, 9, 4 * f, 1, 4 * f, f)]
+        dsts = []
+        for k in range(1, 6):
+            conv = getattr(rdb, f"conv{k}")
+            dw = self._gv(grads, conv.weight)
+            sc = s5 if k == 5 else 1.0
+            for d in range(3):
+                dsts.append((dw, f, k * f, 0, min(k * f, 4 * f), d, 0, (k - 1) * f, sc, 0, 0))
+            if k == 5:
+                dsts.append((dw, f, 5 * f, 4 * f, 5 * f, 3, 0, 0, sc, 0, 0))
+            if conv.bias is not None:
+                ops.colsum(G, (k - 1) * f, f, self._gv(grads, conv.bias), scale=sc)
+        ops.conv3x3_wgrad(A, G, roles, dsts)
+
+    def backward(self, bufs, generation: int, x: torch.Tensor, gout: torch.Tensor, need_x_grad: bool):
+        if generation != self.generation:
+            raise RuntimeError("backward through a GeneratorRRDB forward whose saved activations were overwritten by a "
+                               "later forward (run backward before the next training-mode forward)")
+        g, f, kc, a = self.gen, self.nf, self.kc, self.arena
+        gout = gout.contiguous().float()
+        x = x.contiguous().float()
+        grads = self._grad_views(x.device)
+        pre = bufs["pre"]
+        # flipped / transposed conv_last filter: data gradient of an F->1 conv is a 1->F stencil (288 floats)
+        wt_last = g.conv_last.weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous()
+        dw_last = self._gv(grads, g.conv_last.weight)
+        db_last = self._gv(grads, g.conv_last.bias) if g.conv_last.bias is not None else None
+        if self.kind == "dn":
+            feat_in = bufs["trunk"]
+            ops.conv_first(gout, wt_last, None, bufs["d_trunk"], 0, gate=pre)
+            ops.edge_wgrad(gout, feat_in, 0, f, dw_last.view(g.out_channels, f, 9), ssum=db_last, gate=pre)
+        else:
+            hr = bufs["hr"]
+            ops.conv_first(gout, wt_last, None, bufs["d_hr"], 0, gate=pre, mask=hr, mask_coff=0, mask_slope=0.2)
+            ops.edge_wgrad(gout, hr, 0, f, dw_last.view(g.out_channels, f, 9), ssum=db_last, gate=pre)
+            ups = [bufs["trunk"]] + [bufs[f"up{s}"] for s in range(self.num_upsample)]
+            self._single_conv_wgrad(g.HRconv, ups[-1], bufs["d_hr"], grads)
+            dy = bufs["d_hr"]
+            blob = "d.hr"
+            nin = f
+            for s in range(self.num_upsample - 1, -1, -1):
+                # gradient w.r.t. the shuffled, LeakyReLU(0.01)-activated upsample output, stored un-shuffled
+                ops.conv3x3(dy, 0, nin, a.ptr(blob), kc, f, bufs[f"d_up{s}"], 0, mask=ups[s + 1], mask_coff=0,
+                            mask_slope=0.01, pixel_shuffle=2)
+                dy, blob, nin = bufs[f"d_up{s}"], f"d.up{s}", 4 * f
+                self._single_conv_wgrad(g.upsampling[3 * s], ups[s], dy, grads, perm=1)
+                if s > 0:
+                    raise NotImplementedError("backward through more than one upsampling stage is not built yet")
+            ops.conv3x3(dy, 0, nin, a.ptr(blob), kc, f, bufs["d_trunk"], 0)
+        d_trunk = bufs["d_trunk"]  # dL/d(fea + trunk_conv(...)): feeds trunk_conv and the `fea` skip
+        last_act = bufs["act"][3 * self.nb]
+        self._single_conv_wgrad(g.trunk_conv, last_act, d_trunk, grads)
+        ring = bufs["ring"]
+        d_fea = bufs["d_fea"]
+        if self.nb > 0:
+            ops.conv3x3(d_trunk, 0, f, a.ptr("d.trunk"), kc, f, ring[2], 4 * f)  # E_{nb-1}
+            for i in range(self.nb - 1, -1, -1):
+                for r in (2, 1, 0):
+                    self._rdb_backward(i, r, bufs, grads, d_fea)
+                    self._rdb_wgrad(i, r, bufs, grads)
+        else:
+            ops.conv3x3(d_trunk, 0, f, a.ptr("d.trunk"), kc, f, d_fea, 0)
+        # conv_first: dL/d(fea) = d_fea (through the RRDBs) + d_trunk (skip)
+        cin = g.in_channels
+        r_first = torch.zeros(cin, f, 9, dtype=torch.float32, device=x.device)
+        ops.edge_wgrad(x, d_fea, 0, f, r_first, v2=d_trunk, v2_coff=0)
+        self._gv(grads, g.conv_first.weight).copy_(r_first.flip(2).permute(1, 0, 2).reshape(f, cin, 3, 3))
+        if g.conv_first.bias is not None:
+            dbf = self._gv(grads, g.conv_first.bias)
+            ops.colsum(d_fea, 0, f, dbf)
+            ops.colsum(d_trunk, 0, f, dbf, accumulate=True)
+        gx = None
+        if need_x_grad:
+            # dL/dx = conv_first^T(dL/dfea) (+ the DN residual path); an F->cin stencil = conv_last kernel
+            wt_first = g.conv_first.weight.detach().flip(2, 3).permute(1, 0, 2, 3).contiguous()
+            gx1 = torch.empty_like(x)
+            base = None
+            if self.kind == "dn":
+                base = torch.where((pre >= 0) & (pre <= 1), gout, torch.zeros_like(gout))
+            ops.conv_last(d_fea, 0, wt_first, None, gx1, residual=base, clamp=False)
+            gx = torch.empty_like(x)
+            ops.conv_last(d_trunk, 0, wt_first, None, gx, residual=gx1, clamp=False)
+        return gx, grads

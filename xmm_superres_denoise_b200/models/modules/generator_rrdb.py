@@ -50,10 +50,15 @@ class _GeneratorRRDB(nn.Module):
         state["_engine"] = None  # device buffers and packed weights are rebuilt on first use
         return state
 
-    def _get_engine(self):
-        if self._engine is None:
-            from ...engine import RRDBEngine
+    def _get_engine(self, train: bool = False):
+        from ...engine import RRDBEngine
 
+        if train:
+            from ...engine_train import TrainEngine
+
+            if not isinstance(self._engine, TrainEngine):
+                self._engine = TrainEngine(self, self._kind)
+        elif self._engine is None:
             self._engine = RRDBEngine(self, self._kind)
         return self._engine
 
