@@ -218,6 +218,87 @@ typedef struct {
 } xmm_edge_wgrad_params;
 int xmm_edge_wgrad(const xmm_edge_wgrad_params* p, void* stream);
 
+/* Loss terms ------------------------------------------------------------------------- */
+/* Per-scale record kept on the device by the (MS-)SSIM kernels (12 floats). */
+typedef struct {
+  float minp, maxp, mint, maxt;  /* ranges of preds / target                                */
+  float nmaxp, nminp;            /* #pixels of preds equal to its max / min                  */
+  float dr, c1, c2;              /* data range, (k1*dr)^2, (k2*dr)^2                         */
+  float use_p;                   /* 1 if dr is preds' range (gradient flows into arg-max/min) */
+  float d_dr;                    /* dL/d(dr), written by xmm_msssim_finalize                  */
+  float pad;
+} xmm_scale_stats;
+
+/* One pass over preds/target (fp32, n elements): sums[0..6] = { sum|p-t|, sum(p - t*log(p+1e-8)),
+ * sum (p-t)^2, min p, max p, min t, max t } (deterministic two-stage reduction), and, if `stats`
+ * is given, the range fields of that record.  Replaces torchmetrics MeanAbsoluteError /
+ * PeakSignalNoiseRatio updates and F.poisson_nll_loss (utils/loss_functions.py:15-21,
+ * metrics/metrics.py:36-38).  workspace: xmm_loss_workspace_floats() floats.               */
+size_t xmm_loss_workspace_floats(void);
+int xmm_loss_reduce(const float* preds, const float* target, size_t n, float* sums_dev,
+                    xmm_scale_stats* stats_dev, float* workspace, void* stream);
+/* grad (=|+=) gl * ( coef[0]*sign(p-t) + coef[1]*(1 - t/(p+1e-8)) + coef[2]*(p-t) ); coef_dev and
+ * gl_dev (may be NULL = 1) live on the device, so no host synchronisation is needed.          */
+int xmm_loss_grad(const float* preds, const float* target, size_t n, const float* coef_dev,
+                  const float* gl_dev, float* grad, int accumulate, void* stream);
+/* 2x2 average pooling of preds and target at once (next MS-SSIM scale).                      */
+int xmm_avgpool2_pair(const float* preds, const float* target, float* preds_out, float* target_out,
+                      int nimg, int h, int w, void* stream);
+/* After xmm_loss_reduce filled the ranges: SSIM constants c1,c2 and the arg-max/arg-min counts. */
+int xmm_ssim_prepare(const float* preds, size_t n, xmm_scale_stats* stats_dev, float k1, float k2,
+                     void* stream);
+
+/* SSIM statistics of one scale (19-tap Gaussian, sigma from the window the caller passes).
+ * Forward (kimg == NULL): acc[img][tile][4] partial sums {ssim, cs, d sel/dc1, d sel/dc2}.
+ * Backward (kimg != NULL): ga/gb/gc[img][h-18][w-18] = kimg[img] * d sel/d{mu_p, E[pp], E[pt]}. */
+typedef struct {
+  const float* preds; const float* target;
+  int nimg, h, w;
+  const xmm_scale_stats* stats_dev;
+  float window[19];
+  int use_sim;          /* 1: the ssim map feeds this scale's value, 0: the contrast-structure map */
+  float* acc;           /* forward output, xmm_ssim_tiles(h,w)*nimg*4 floats                      */
+  const float* kimg;    /* backward: per-image coefficients                                       */
+  float* ga; float* gb; float* gc;
+} xmm_ssim_stats_params;
+int xmm_ssim_tiles(int h, int w);
+int xmm_ssim_stats(const xmm_ssim_stats_params* p, void* stream);
+
+/* Gradient w.r.t. preds of one scale: transposed Gaussian of ga/gb/gc combined with p and t,
+ * plus 1/4 of the coarser scale's gradient (avg-pool backward) and the data-range term.      */
+typedef struct {
+  const float* preds; const float* target;
+  int nimg, h, w;
+  const xmm_scale_stats* stats_dev;
+  float window[19];
+  const float* ga; const float* gb; const float* gc;
+  const float* coarse;  /* [nimg][h/2][w/2] or NULL                                            */
+  float* grad;          /* [nimg][h][w]                                                        */
+  int accumulate;
+} xmm_ssim_grad_params;
+int xmm_ssim_grad(const xmm_ssim_grad_params* p, void* stream);
+
+/* Combine the per-scale sums: value = mean_b prod_s relu(v_{b,s})^beta_s (nscales == 1: plain SSIM
+ * mean), img_val[b], backward coefficients kimg[s][img] (including gl * weight / batch) and
+ * stats[s].d_dr.  MultiScaleStructuralSimilarityIndexMeasure / StructuralSimilarityIndexMeasure
+ * batch values (utils/loss_functions.py:19-20,33).                                            */
+typedef struct {
+  const float* acc[5];
+  int tiles[5];
+  int nvalid[5];
+  int nscales;
+  int batch, channels;
+  float betas[5];
+  float k1, k2;
+  xmm_scale_stats* stats_dev;
+  float* value;
+  float* img_val;
+  float* kimg;
+  const float* gl_dev;
+  float weight;
+} xmm_msssim_finalize_params;
+int xmm_msssim_finalize(const xmm_msssim_finalize_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

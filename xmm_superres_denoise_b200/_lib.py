@@ -85,7 +85,33 @@ class EdgeWgradParams(Structure):
                 ("batch", c_int), ("ns", c_int), ("height", c_int), ("width", c_int), ("channels", c_int)]
 
 
-EXTRA_STRUCTS = {"xmm_wgrad_role": WgradRole, "xmm_wgrad_dst": WgradDst, "xmm_wgrad_params": WgradParams,
+class ScaleStats(Structure):
+    _fields_ = [(n, c_float) for n in ("minp", "maxp", "mint", "maxt", "nmaxp", "nminp", "dr", "c1", "c2", "use_p",
+                                       "d_dr", "pad")]
+
+
+class SsimStatsParams(Structure):
+    _fields_ = [("preds", c_void_p), ("target", c_void_p), ("nimg", c_int), ("h", c_int), ("w", c_int),
+                ("stats_dev", c_void_p), ("window", c_float * 19), ("use_sim", c_int), ("acc", c_void_p),
+                ("kimg", c_void_p), ("ga", c_void_p), ("gb", c_void_p), ("gc", c_void_p)]
+
+
+class SsimGradParams(Structure):
+    _fields_ = [("preds", c_void_p), ("target", c_void_p), ("nimg", c_int), ("h", c_int), ("w", c_int),
+                ("stats_dev", c_void_p), ("window", c_float * 19), ("ga", c_void_p), ("gb", c_void_p),
+                ("gc", c_void_p), ("coarse", c_void_p), ("grad", c_void_p), ("accumulate", c_int)]
+
+
+class MsssimFinalizeParams(Structure):
+    _fields_ = [("acc", c_void_p * 5), ("tiles", c_int * 5), ("nvalid", c_int * 5), ("nscales", c_int),
+                ("batch", c_int), ("channels", c_int), ("betas", c_float * 5), ("k1", c_float), ("k2", c_float),
+                ("stats_dev", c_void_p), ("value", c_void_p), ("img_val", c_void_p), ("kimg", c_void_p),
+                ("gl_dev", c_void_p), ("weight", c_float)]
+
+
+EXTRA_STRUCTS = {"xmm_scale_stats": ScaleStats, "xmm_ssim_stats_params": SsimStatsParams,
+                 "xmm_ssim_grad_params": SsimGradParams, "xmm_msssim_finalize_params": MsssimFinalizeParams,
+                 "xmm_wgrad_role": WgradRole, "xmm_wgrad_dst": WgradDst, "xmm_wgrad_params": WgradParams,
                  "xmm_edge_wgrad_params": EdgeWgradParams}
 
 # name -> (restype, argtypes); the non-GPU test-suite checks every name in include/xmm_b200.h is here
@@ -106,6 +132,15 @@ SIGNATURES = {
     "xmm_conv3x3_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "xmm_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_float, c_int, c_void_p]),
     "xmm_edge_wgrad": (c_int, [POINTER(EdgeWgradParams), c_void_p]),
+    "xmm_loss_workspace_floats": (c_size_t, []),
+    "xmm_loss_reduce": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xmm_loss_grad": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "xmm_avgpool2_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "xmm_ssim_prepare": (c_int, [c_void_p, c_size_t, c_void_p, c_float, c_float, c_void_p]),
+    "xmm_ssim_tiles": (c_int, [c_int, c_int]),
+    "xmm_ssim_stats": (c_int, [POINTER(SsimStatsParams), c_void_p]),
+    "xmm_ssim_grad": (c_int, [POINTER(SsimGradParams), c_void_p]),
+    "xmm_msssim_finalize": (c_int, [POINTER(MsssimFinalizeParams), c_void_p]),
 }
 
 _lib = None

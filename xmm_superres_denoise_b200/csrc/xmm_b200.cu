@@ -6,6 +6,7 @@
 #include "conv3x3_tc.cuh"
 #include "edge_kernels.cuh"
 #include "host_common.cuh"
+#include "loss_kernels.cuh"
 #include "pack_weights.cuh"
 #include "wgrad_tc.cuh"
 
@@ -437,6 +438,144 @@ extern "C" int xmm_edge_wgrad(const xmm_edge_wgrad_params* pp, void* stream) {
   if (p.channels == 32) edge_wgrad_kernel<32><<<grid, 32 * 9, 0, s>>>(a);
   else if (p.channels == 64) edge_wgrad_kernel<64><<<grid, 64 * 9, 0, s>>>(a);
   else return fail(XMM_ERR_UNSUPPORTED_SHAPE, "edge_wgrad: channels=%d (supported: 32, 64)", p.channels);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+// ----------------------------------------------------------------------------- losses
+static_assert(sizeof(xmm_scale_stats) == sizeof(ScaleStats), "xmm_scale_stats mirrors ScaleStats");
+static const int kLossBlocks = 592;  // 4 x 148
+
+extern "C" size_t xmm_loss_workspace_floats(void) { return size_t(kLossBlocks) * 8; }
+
+extern "C" int xmm_loss_reduce(const float* preds, const float* target, size_t n, float* sums_dev,
+                               xmm_scale_stats* stats_dev, float* workspace, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(preds && target && workspace && n > 0, "loss_reduce: null pointer or empty input");
+  XMM_REQUIRE((reinterpret_cast<uintptr_t>(preds) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0,
+              "loss_reduce: pointers must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  size_t need = (n + 1023) / 1024;
+  const int blocks = int(need < size_t(kLossBlocks) ? need : size_t(kLossBlocks));
+  loss_reduce_kernel<<<blocks, 256, 0, s>>>(preds, target, n, workspace);
+  XMM_CUDA_OK(cudaGetLastError());
+  loss_reduce_finalize_kernel<<<1, 32, 0, s>>>(workspace, blocks, sums_dev, reinterpret_cast<ScaleStats*>(stats_dev));
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_loss_grad(const float* preds, const float* target, size_t n, const float* coef_dev,
+                             const float* gl_dev, float* grad, int accumulate, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(preds && target && coef_dev && grad, "loss_grad: null pointer");
+  if (n == 0) return XMM_OK;
+  loss_grad_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(preds, target, n, coef_dev,
+                                                                                            gl_dev, grad, accumulate);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_avgpool2_pair(const float* preds, const float* target, float* preds_out, float* target_out,
+                                 int nimg, int h, int w, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(preds && target && preds_out && target_out, "avgpool2: null pointer");
+  const size_t n = size_t(nimg) * (h / 2) * (w / 2);
+  if (n == 0) return XMM_OK;
+  avgpool2_pair_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      preds, target, preds_out, target_out, nimg, h, w);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_ssim_prepare(const float* preds, size_t n, xmm_scale_stats* stats_dev, float k1, float k2,
+                                void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(preds && stats_dev && n > 0, "ssim_prepare: null pointer or empty input");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ssim_constants_kernel<<<1, 32, 0, s>>>(reinterpret_cast<ScaleStats*>(stats_dev), k1, k2);
+  XMM_CUDA_OK(cudaGetLastError());
+  size_t need = (n + 255) / 256;
+  const int blocks = int(need < size_t(kLossBlocks) ? need : size_t(kLossBlocks));
+  count_ties_kernel<<<blocks, 256, 0, s>>>(preds, n, reinterpret_cast<ScaleStats*>(stats_dev));
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_ssim_tiles(int h, int w) {
+  const int vh = h - 2 * kSsimPad, vw = w - 2 * kSsimPad;
+  if (vh <= 0 || vw <= 0) return 0;
+  return ((vh + kSsimTileH - 1) / kSsimTileH) * ((vw + kSsimTileW - 1) / kSsimTileW);
+}
+
+extern "C" int xmm_ssim_stats(const xmm_ssim_stats_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "ssim_stats: null params");
+  const xmm_ssim_stats_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.preds && p.target && p.stats_dev, "ssim_stats: null pointer");
+  XMM_REQUIRE(p.h > 2 * kSsimPad && p.w > 2 * kSsimPad && p.nimg > 0 && p.nimg <= 65535,
+              "ssim_stats: image %dx%d is not larger than the %d-tap Gaussian window", p.h, p.w, kSsimTaps);
+  XMM_REQUIRE((p.kimg == nullptr) == (p.acc != nullptr), "ssim_stats: give acc (forward) or kimg+ga/gb/gc (backward)");
+  XMM_REQUIRE(p.kimg == nullptr || (p.ga && p.gb && p.gc), "ssim_stats: backward needs ga, gb, gc");
+  SsimArgs a{};
+  a.p = p.preds; a.t = p.target; a.nimg = p.nimg; a.h = p.h; a.w = p.w;
+  a.st = reinterpret_cast<const ScaleStats*>(p.stats_dev);
+  for (int i = 0; i < kSsimTaps; ++i) a.win.w[i] = p.window[i];
+  a.acc = p.acc; a.use_sim = p.use_sim; a.kimg = p.kimg; a.ga = p.ga; a.gb = p.gb; a.gc = p.gc;
+  const int vh = p.h - 2 * kSsimPad, vw = p.w - 2 * kSsimPad;
+  dim3 grid((vw + kSsimTileW - 1) / kSsimTileW, (vh + kSsimTileH - 1) / kSsimTileH, p.nimg);
+  ssim_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_ssim_grad(const xmm_ssim_grad_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "ssim_grad: null params");
+  const xmm_ssim_grad_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.preds && p.target && p.stats_dev && p.ga && p.gb && p.gc && p.grad, "ssim_grad: null pointer");
+  XMM_REQUIRE(p.h > 2 * kSsimPad && p.w > 2 * kSsimPad && p.nimg > 0 && p.nimg <= 65535, "ssim_grad: bad shape");
+  SsimGradArgs a{};
+  a.p = p.preds; a.t = p.target; a.nimg = p.nimg; a.h = p.h; a.w = p.w;
+  a.st = reinterpret_cast<const ScaleStats*>(p.stats_dev);
+  for (int i = 0; i < kSsimTaps; ++i) a.win.w[i] = p.window[i];
+  a.ga = p.ga; a.gb = p.gb; a.gc = p.gc; a.coarse = p.coarse; a.grad = p.grad; a.accumulate = p.accumulate;
+  dim3 grid((p.w + kSsimTileW - 1) / kSsimTileW, (p.h + kSsimTileH - 1) / kSsimTileH, p.nimg);
+  ssim_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_msssim_finalize(const xmm_msssim_finalize_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "msssim_finalize: null params");
+  const xmm_msssim_finalize_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.nscales >= 1 && p.nscales <= kMaxScales && p.batch >= 1 && p.batch <= 1024 && p.channels >= 1,
+              "msssim_finalize: %d scales, batch %d", p.nscales, p.batch);
+  XMM_REQUIRE(p.stats_dev && p.value && p.img_val && p.kimg, "msssim_finalize: null pointer");
+  MsFinalizeArgs a{};
+  for (int s = 0; s < p.nscales; ++s) {
+    XMM_REQUIRE(p.acc[s] && p.tiles[s] > 0 && p.nvalid[s] > 0, "msssim_finalize: scale %d is empty", s);
+    a.acc[s] = p.acc[s]; a.tiles[s] = p.tiles[s]; a.nvalid[s] = p.nvalid[s]; a.betas[s] = p.betas[s];
+  }
+  a.nscales = p.nscales; a.batch = p.batch; a.channels = p.channels; a.k1 = p.k1; a.k2 = p.k2;
+  a.st = reinterpret_cast<ScaleStats*>(p.stats_dev);
+  a.value = p.value; a.img_val = p.img_val; a.kimg = p.kimg; a.gl = p.gl_dev; a.weight = p.weight;
+  const int threads = ((p.batch + 31) / 32) * 32;
+  msssim_finalize_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
