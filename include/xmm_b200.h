@@ -299,6 +299,13 @@ typedef struct {
 } xmm_msssim_finalize_params;
 int xmm_msssim_finalize(const xmm_msssim_finalize_params* p, void* stream);
 
+/* Optimizer -------------------------------------------------------------------------- */
+/* One Adam step (torch.optim.Adam semantics: models/model.py:239-247, res/configs/models.toml:7-8)
+ * over a flat fp32 parameter buffer; `step` is the 1-based step count; grad is multiplied by
+ * grad_scale first (1/world_size after a sum all-reduce).                                     */
+int xmm_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                  float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

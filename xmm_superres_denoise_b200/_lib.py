@@ -141,6 +141,8 @@ SIGNATURES = {
     "xmm_ssim_stats": (c_int, [POINTER(SsimStatsParams), c_void_p]),
     "xmm_ssim_grad": (c_int, [POINTER(SsimGradParams), c_void_p]),
     "xmm_msssim_finalize": (c_int, [POINTER(MsssimFinalizeParams), c_void_p]),
+    "xmm_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float,
+                              c_int, c_float, c_void_p]),
 }
 
 _lib = None

@@ -252,6 +252,25 @@ __global__ void __launch_bounds__(128) conv_last_kernel(const ConvLastArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------ fused Adam
+// torch.optim.Adam (models/model.py:239-247; no weight decay, no amsgrad) over ONE flat fp32 buffer
+// holding every parameter of the generator: a single launch instead of ~130 per-tensor updates.
+//   g = grad * grad_scale (1/world_size after the all-reduce)
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float grad_scale) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gv = g[i] * grad_scale;
+  const float mv = b1 * m[i] + (1.0f - b1) * gv;
+  const float vv = b2 * v[i] + (1.0f - b2) * gv * gv;
+  m[i] = mv;
+  v[i] = vv;
+  const float denom = sqrtf(vv) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mv / denom);
+}
+
 // ------------------------------------------------------------------------------ edge weight grads
 // R[o][c][tap] (+)= sum_p s[o][p] * (V[p + off(tap)][c] + V2[p + off(tap)][c]),   S[o] (+)= sum_p s[o][p]
 // with s an fp32 NCHW image (optionally gated by the forward clamp) and V a bf16 NHWC window.

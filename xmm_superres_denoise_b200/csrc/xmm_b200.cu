@@ -579,3 +579,20 @@ extern "C" int xmm_msssim_finalize(const xmm_msssim_finalize_params* pp, void* s
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
+
+// ----------------------------------------------------------------------------- optimizer
+extern "C" int xmm_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                             float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(params && grads && exp_avg && exp_avg_sq, "adam: null pointer");
+  XMM_REQUIRE(step >= 1, "adam: step count starts at 1 (got %d)", step);
+  if (n == 0) return XMM_OK;
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  adam_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, float(bc1), float(sqrt(bc2)), grad_scale);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}

@@ -73,6 +73,10 @@ class WeightArena:
         self.blobs[blob.name] = blob
         self._order.append(blob)
 
+    def invalidate(self) -> None:
+        """Force a re-pack on the next ensure() (for writers that bypass tensor version counters)."""
+        self._versions = None
+
     def ptr(self, name: str) -> int:
         assert self._arena is not None
         return self._arena.data_ptr() + self.blobs[name].offset

@@ -184,7 +184,8 @@ class TrainEngine(RRDBEngine):
                 ops.colsum(G, (k - 1) * f, f, self._gv(grads, conv.bias), scale=sc)
         ops.conv3x3_wgrad(A, G, roles, dsts)
 
-    def backward(self, bufs, generation: int, x: torch.Tensor, gout: torch.Tensor, need_x_grad: bool):
+    def backward(self, bufs, generation: int, x: torch.Tensor, gout: torch.Tensor, need_x_grad: bool,
+                 rrdb_done_hook=None):
         if generation != self.generation:
             raise RuntimeError("backward through a GeneratorRRDB forward whose saved activations were overwritten by a "
                                "later forward (run backward before the next training-mode forward)")
@@ -230,6 +231,8 @@ class TrainEngine(RRDBEngine):
                 for r in (2, 1, 0):
                     self._rdb_backward(i, r, bufs, grads, d_fea)
                     self._rdb_wgrad(i, r, bufs, grads)
+                if rrdb_done_hook is not None:  # every gradient of RRDB i (and of all later layers) is enqueued
+                    rrdb_done_hook(i, self.last_flat_grad)
         else:
             ops.conv3x3(d_trunk, 0, f, a.ptr("d.trunk"), kc, f, d_fea, 0)
         # conv_first: dL/d(fea) = d_fea (through the RRDBs) + d_trunk (skip)

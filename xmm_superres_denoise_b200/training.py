@@ -1,0 +1,165 @@
+"""Plain-torch training loop for the RRDB path (what ``lightning.Trainer.fit`` + ``Model.training_step``
++ ``configure_optimizers`` do in the reference: train.py:148-165, models/model.py:51-86,239-247), with the
+pieces the reference leaves to Lightning made explicit and B200-native:
+
+* data parallel: one process per GPU, the batch is already sharded by the caller; gradients live in ONE
+  flat fp32 buffer that is all-reduced with NCCL in chunks (one per RRDB, released as soon as that RRDB's
+  weight gradients have been enqueued) on a side stream, overlapping the rest of the backward pass;
+* optimizer: Adam on ONE flat fp32 parameter buffer (single kernel), after which the packed bf16
+  tensor-core weight images are rebuilt by the engine's single repack launch on the next forward.
+
+``TrainStep`` talks to the engine directly (no autograd graph); the autograd path
+(``loss(model(x)).backward()``) stays available for Lightning / DDP users and is tested to give the same
+gradients.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+
+
+def flatten_parameters(module: nn.Module) -> torch.Tensor:
+    """Re-point every parameter of `module` at a slice of one contiguous fp32 buffer (in place:
+    Parameter objects, names and shapes are unchanged, so state_dict / optimizers / DDP keep working)."""
+    params = list(module.parameters())
+    if not params:
+        raise ValueError("module has no parameters")
+    dev = params[0].device
+    if any(p.device != dev or p.dtype != torch.float32 for p in params):
+        raise RuntimeError("flatten_parameters needs fp32 parameters on one device")
+    flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            n = p.numel()
+            view = flat[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            off += n
+    return flat
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank` (inference shards images, no collective)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place mean all-reduce of a flat gradient buffer (NCCL on CUDA tensors, gloo on CPU tensors)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(dist.get_world_size(group))
+    return flat
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics on a flat parameter buffer (one kernel per step)."""
+
+    def __init__(self, flat_params: torch.Tensor, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 on_update=None) -> None:
+        _lib.require_cuda_tensor(flat_params, torch.float32, "FusedAdam parameters")
+        self.params = flat_params
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = torch.zeros_like(flat_params)
+        self.exp_avg_sq = torch.zeros_like(flat_params)
+        self.step_count = 0
+        # the kernel writes through raw pointers, which no tensor version counter sees: the owner of packed
+        # copies of these parameters (engine.WeightArena) must be told explicitly
+        self.on_update = on_update
+
+    def step(self, flat_grads: torch.Tensor, grad_scale: float = 1.0) -> None:
+        _lib.require_cuda_tensor(flat_grads, torch.float32, "FusedAdam gradients")
+        if flat_grads.numel() != self.params.numel():
+            raise RuntimeError("gradient buffer size does not match the parameter buffer")
+        self.step_count += 1
+        _lib.check(_lib.load().xmm_adam_step(self.params.data_ptr(), flat_grads.data_ptr(), self.exp_avg.data_ptr(),
+                                             self.exp_avg_sq.data_ptr(), self.params.numel(), self.lr, self.betas[0],
+                                             self.betas[1], self.eps, self.step_count, grad_scale, _lib.stream_ptr()))
+        ops._count()
+        if self.on_update is not None:
+            self.on_update()
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr,
+                "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd) -> None:
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+
+class TrainStep:
+    """forward + loss + backward + gradient all-reduce + Adam for one (lr, hr) batch."""
+
+    def __init__(self, model: nn.Module, loss, lr: float = 1e-4, betas=(0.9, 0.999), group=None,
+                 overlap_allreduce: bool = True) -> None:
+        import torch.distributed as dist
+
+        self.model, self.loss, self.group = model, loss, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.flat = flatten_parameters(model)
+        self.engine = model._get_engine(train=True)
+        self.opt = FusedAdam(self.flat, lr, betas, on_update=self.engine.arena.invalidate)
+        self.overlap = overlap_allreduce and self.world > 1
+        self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.overlap else None
+        self._works: List = []
+        self._ones = torch.ones(1, dtype=torch.float32, device=self.flat.device)
+        # chunk boundaries of the flat buffer: one chunk per RRDB (parameters are registered in module order)
+        self._chunks = self._rrdb_chunks()
+
+    def _rrdb_chunks(self):
+        offs, off = {}, 0
+        for name, p in self.model.named_parameters():
+            offs[name] = (off, off + p.numel())
+            off += p.numel()
+        chunks = {}
+        for i in range(self.model.num_res_blocks):
+            names = [n for n in offs if n.startswith(f"rrdb.{i}.")]
+            chunks[i] = (min(offs[n][0] for n in names), max(offs[n][1] for n in names))
+        return chunks
+
+    def _allreduce_range(self, flat_grad: torch.Tensor, lo: int, hi: int) -> None:
+        import torch.distributed as dist
+
+        if self.world == 1 or hi <= lo:
+            return
+        if self.overlap:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self._works.append(dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                                   async_op=True))
+        else:
+            dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+    def __call__(self, lr_img: torch.Tensor, hr_img: torch.Tensor) -> torch.Tensor:
+        eng = self.engine
+        out, bufs = eng.forward_train(lr_img)
+        # Model.forward's second clamp (models/model.py:49) is the identity on an output already in [0,1]
+        st = self.loss._evaluate(out, hr_img.contiguous().float())
+        self.loss._merge(st)
+        gout = self.loss._gradient(out, hr_img.contiguous().float(), st, self._ones)
+        done = [len(self.flat)]  # upper end of the not-yet-reduced tail of the flat buffer
+
+        def hook(rrdb_index: int, flat_grad: torch.Tensor) -> None:
+            lo, _ = self._chunks[rrdb_index]
+            self._allreduce_range(flat_grad, lo, done[0])  # this RRDB and everything after it not yet sent
+            done[0] = lo
+
+        _, _ = eng.backward(bufs, eng.generation, lr_img, gout, need_x_grad=False,
+                            rrdb_done_hook=hook if self.world > 1 else None)
+        flat_grad = eng.last_flat_grad
+        self._allreduce_range(flat_grad, 0, done[0])
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        self.opt.step(flat_grad, 1.0 / self.world)
+        return st["total"]
