@@ -434,7 +434,7 @@ def main() -> None:
                      "launches_timed": n_k, "share_of_step": k_ms / ms_total, "traffic": None,
                      "whole_step_tflops": total_flop * args.steps / (ms_total * 1e-3) / 1e12},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         threads = os.cpu_count() or 1
         ips, dt = cpu_infer_sample(8, threads)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",

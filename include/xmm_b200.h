@@ -51,8 +51,10 @@ typedef struct {
   int src_cin;
   int o_off, i_off;
   int transpose;
-  int k_off, k_count;
+  int k_off, k_count;  /* K positions [k_off, k_off+k_count) of the packed layer                */
   float scale;
+  int n_off, n_count;  /* rows [n_off, n_off+n_count) of the packed layer; the segment's own row
+                          index is n - n_off                                                    */
 } xmm_pack_segment;
 
 typedef struct {
@@ -64,6 +66,7 @@ typedef struct {
   int nseg;           /* 1..5                                                              */
   int perm;           /* 1: PixelShuffle(2) channel permutation on the O index             */
   int n_valid;        /* rows >= n_valid are zero                                          */
+  int bias_n;         /* rows < bias_n take bias[seg[0].o_off + row]; the rest get 0               */
   xmm_pack_segment seg[5];
 } xmm_pack_job;
 

@@ -164,7 +164,8 @@ static double run_conv_case(const ConvCase& c, int tap_mode, bool verbose) {
   job.nseg = 1;
   job.perm = c.shuffle ? 1 : 0;
   job.n_valid = c.cout;
-  job.seg[0] = xmm_pack_segment{w_d, c.cin, 0, 0, 0, 0, c.cin, 1.0f};
+  job.bias_n = c.cout;
+  job.seg[0] = xmm_pack_segment{w_d, c.cin, 0, 0, 0, 0, c.cin, 1.0f, 0, c.cout};
   xmm_pack_job* job_d;
   CK(cudaMalloc(&job_d, sizeof(job)));
   CK(cudaMemcpy(job_d, &job, sizeof(job), cudaMemcpyHostToDevice));
@@ -272,7 +273,8 @@ static void time_conv(int B, int H, int W, int F, int k, int kc, int tap_mode, i
   xmm_pack_job job{};
   job.dst = blob; job.nt = cout; job.kc = kc; job.nchunks = nchunks; job.nseg = 1; job.n_valid = cout;
   job.perm = shuffle;
-  job.seg[0] = xmm_pack_segment{w_d, cin, 0, 0, 0, 0, cin, 1.0f};
+  job.bias_n = cout;
+  job.seg[0] = xmm_pack_segment{w_d, cin, 0, 0, 0, 0, cin, 1.0f, 0, cout};
   xmm_pack_job* job_d;
   CK(cudaMalloc(&job_d, sizeof(job)));
   CK(cudaMemcpy(job_d, &job, sizeof(job), cudaMemcpyHostToDevice));

@@ -17,12 +17,12 @@ LIB_PATH = os.path.join(_HERE, "libxmm_b200.so")
 
 class PackSegment(Structure):
     _fields_ = [("src", c_void_p), ("src_cin", c_int), ("o_off", c_int), ("i_off", c_int), ("transpose", c_int),
-                ("k_off", c_int), ("k_count", c_int), ("scale", c_float)]
+                ("k_off", c_int), ("k_count", c_int), ("scale", c_float), ("n_off", c_int), ("n_count", c_int)]
 
 
 class PackJob(Structure):
     _fields_ = [("dst", c_void_p), ("bias", c_void_p), ("nt", c_int), ("kc", c_int), ("nchunks", c_int),
-                ("nseg", c_int), ("perm", c_int), ("n_valid", c_int), ("seg", PackSegment * 5)]
+                ("nseg", c_int), ("perm", c_int), ("n_valid", c_int), ("bias_n", c_int), ("seg", PackSegment * 5)]
 
 
 class Conv3x3Params(Structure):

@@ -30,16 +30,17 @@ __global__ void pack_jobs_kernel(const xmm_pack_job* __restrict__ jobs) {
       if (n < job.n_valid) {
         for (int s = 0; s < job.nseg; ++s) {
           const xmm_pack_segment& sg = job.seg[s];
-          if (kg >= sg.k_off && kg < sg.k_off + sg.k_count) {
+          if (kg >= sg.k_off && kg < sg.k_off + sg.k_count && n >= sg.n_off && n < sg.n_off + sg.n_count) {
             const int c = kg - sg.k_off;
+            const int nn = n - sg.n_off;
             int o, i, t;
             if (!sg.transpose) {
-              o = sg.o_off + (job.perm ? shuffle_perm(n, job.nt / 4) : n);
+              o = sg.o_off + (job.perm ? shuffle_perm(nn, sg.n_count / 4) : nn);
               i = sg.i_off + c;
               t = dy * 3 + dx;
             } else {
               o = sg.o_off + (job.perm ? shuffle_perm(c, sg.k_count / 4) : c);
-              i = sg.i_off + n;
+              i = sg.i_off + nn;
               t = (2 - dy) * 3 + (2 - dx);
             }
             val = sg.scale * sg.src[(size_t(o) * sg.src_cin + i) * 9 + t];
@@ -55,7 +56,7 @@ __global__ void pack_jobs_kernel(const xmm_pack_job* __restrict__ jobs) {
     float* bdst = reinterpret_cast<float*>(dst + size_t(nblocks) * job.nt * rowb);
     for (int n = threadIdx.x; n < job.nt; n += blockDim.x) {
       float b = 0.f;
-      if (job.bias != nullptr && n < job.n_valid && !job.seg[0].transpose) {
+      if (job.bias != nullptr && n < job.n_valid && n < job.bias_n && !job.seg[0].transpose) {
         const int o = job.seg[0].o_off + (job.perm ? shuffle_perm(n, job.nt / 4) : n);
         b = job.bias[o];
       }

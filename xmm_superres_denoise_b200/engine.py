@@ -37,6 +37,8 @@ class _Segment:
     k_off: int
     k_count: int
     scale: float
+    n_off: int = 0
+    n_count: int = -1  # -1: all rows of the blob
 
 
 @dataclass
@@ -49,6 +51,7 @@ class _Blob:
     segments: List[_Segment]
     bias: Optional[torch.Tensor] = None
     perm: int = 0
+    bias_n: int = -1  # rows that take a bias (-1: all)
     offset: int = 0  # byte offset inside the blob arena
 
     @property
@@ -104,11 +107,15 @@ class WeightArena:
                 j.dst = self._arena.data_ptr() + b.offset
                 j.bias = b.bias.data_ptr() if b.bias is not None else None
                 j.nt, j.kc, j.nchunks, j.nseg, j.perm, j.n_valid = b.nt, b.kc, b.nchunks, len(b.segments), b.perm, b.nt
+                j.bias_n = b.nt if b.bias_n < 0 else b.bias_n
+                if len(b.segments) > 5:
+                    raise RuntimeError(f"{b.name}: a packed layer takes at most 5 source segments")
                 for s_c, s in zip(j.seg, b.segments):
                     if s.param.dtype != torch.float32 or not s.param.is_contiguous() or s.param.device != device:
                         raise RuntimeError(f"{b.name}: parameters must be contiguous fp32 tensors on {device}")
                     s_c.src, s_c.src_cin, s_c.o_off, s_c.i_off = s.param.data_ptr(), s.src_cin, s.o_off, s.i_off
                     s_c.transpose, s_c.k_off, s_c.k_count, s_c.scale = s.transpose, s.k_off, s.k_count, s.scale
+                    s_c.n_off, s_c.n_count = s.n_off, (b.nt if s.n_count < 0 else s.n_count)
             raw = bytes(jobs)
             self._jobs_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
             self._key = key
