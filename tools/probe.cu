@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(long long* cycles, in
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tb = tmem_ptr;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && ptx::elect_one()) {
     const uint32_t a_addr = ptx::smem_u32(smem);
     const uint32_t b_addr = a_addr + 16384;
     const uint64_t adesc = ptx::umma_smem_desc(a_addr, 16, 1024, ptx::UMMA_SW128);

@@ -219,7 +219,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t wtot = args.w_bytes + Cfg::kBiasBytes;
       ptx::mbar_expect_tx(w_bar, wtot);
       const uint8_t* gsrc = static_cast<const uint8_t*>(args.wblob);
@@ -252,7 +252,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_wait(w_bar, 0);
       ptx::tc_fence_after();
       const uint32_t w_addr = ptx::smem_u32(w_s);

@@ -14,6 +14,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  tcgen05.mma / cp.async.bulk.tensor take their operands from
+// uniform registers: inside an `if (lane == 0)` branch ptxas cannot prove uniformity and wraps EVERY such
+// instruction in an ELECT/BRA.U.ANY "waterfall" loop (~47 cycles per MMA measured on B200, which caps an
+// M=128,N=32 MMA stream at 34 % of the tensor pipe).  Branching on elect.sync keeps the issue loop straight-line.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -87,7 +87,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int tiles_per_img = args.tiles_x * args.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0 && has_work) {
+    if (has_work && ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_tile; tile < args.num_tiles; tile += role.cta_count) {
@@ -112,7 +112,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work && ptx::elect_one()) {
       const uint32_t idesc = ptx::umma_idesc_bf16_f32(128, role.n, 1, 1);
       const uint32_t a_lbo = role.x_boxes > 1 ? uint32_t(kWgBoxXBytes) : 0u;
       int stage = 0;
