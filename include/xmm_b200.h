@@ -99,7 +99,7 @@ typedef struct {
   void* out; int out_ctot, out_coff;
   int pixel_shuffle;  /* 1: out is [batch][2*height][2*width][out_ctot], cout/4 channels;
                          2: inverse -- out is [batch][height/2][width/2][out_ctot], 4*cout ch. */
-  int tap_mode;       /* 0 = library default; 1..3 force a shared-memory tap layout (probe only) */
+  int tap_mode;       /* 0 = library default; 1..3 force a haloed-tap-view layout, 4 the column-scatter form (probe only) */
 } xmm_conv3x3_params;
 
 int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);

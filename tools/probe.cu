@@ -29,7 +29,9 @@
 using namespace xmm;
 
 // ------------------------------------------------------------------ 1. UMMA rate
-template <int N, bool TS, int KSTEPS>
+// LAYOUT 0: SW128 K-major canonical tile.  1: SW64 canonical (8-row groups 512 B apart).  2: SW64 haloed
+// [18][10]-pixel patch, 9 tap views (SBO = 10 rows) x 2 K-steps -- exactly the conv kernel's A operand stream.
+template <int N, bool TS, int KSTEPS, int LAYOUT = 0>
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(long long* cycles, int iters, int nacc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -50,18 +52,28 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(long long* cycles, in
   if (threadIdx.x < 32 && ptx::elect_one()) {
     const uint32_t a_addr = ptx::smem_u32(smem);
     const uint32_t b_addr = a_addr + 16384;
-    const uint64_t adesc = ptx::umma_smem_desc(a_addr, 16, 1024, ptx::UMMA_SW128);
-    const uint64_t bdesc = ptx::umma_smem_desc(b_addr, 16, 1024, ptx::UMMA_SW128);
+    const uint64_t adesc = LAYOUT == 0   ? ptx::umma_smem_desc(a_addr, 16, 1024, ptx::UMMA_SW128)
+                           : LAYOUT == 1 ? ptx::umma_smem_desc(a_addr, 16, 512, ptx::UMMA_SW64)
+                                         : ptx::umma_smem_desc(0, 16, 640, ptx::UMMA_SW64);
+    const uint64_t bdesc = LAYOUT == 0 ? ptx::umma_smem_desc(b_addr, 16, 1024, ptx::UMMA_SW128)
+                                       : ptx::umma_smem_desc(b_addr, 16, 512, ptx::UMMA_SW64);
     constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(128, N, 0, 0);
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       const uint32_t d = tb + uint32_t((it % nacc) * N);
 #pragma unroll
       for (int ks = 0; ks < KSTEPS; ++ks) {
-        if (TS)
+        if (TS) {
           ptx::umma_ts(d, tb + 448u + uint32_t((ks & 3) * 8), bdesc + uint64_t(((ks & 3) * 32) >> 4), idesc, 1u);
-        else
+        } else if (LAYOUT == 0) {
           ptx::umma_ss(d, adesc + uint64_t(((ks & 3) * 32) >> 4), bdesc + uint64_t(((ks & 3) * 32) >> 4), idesc, 1u);
+        } else if (LAYOUT == 1) {
+          ptx::umma_ss(d, adesc + uint64_t(((ks & 1) * 32) >> 4), bdesc + uint64_t(((ks & 1) * 32) >> 4), idesc, 1u);
+        } else {
+          const int tap = (ks >> 1) % 9, dy = tap / 3, dx = tap % 3;
+          const uint32_t a = a_addr + uint32_t((dy * 10 + dx) * 64 + (ks & 1) * 32);
+          ptx::umma_ss(d, adesc | uint64_t((a & 0x3FFFFu) >> 4), bdesc + uint64_t(((ks & 1) * 32) >> 4), idesc, 1u);
+        }
       }
     }
     ptx::umma_commit(&bar);
@@ -77,16 +89,16 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(long long* cycles, in
   }
 }
 
-template <int N, bool TS>
+template <int N, bool TS, int LAYOUT = 0>
 void run_rate(int nacc) {
   constexpr int KSTEPS = 36;  // one conv K-chunk worth of MMAs between loop overheads
   const int iters = 400;
   long long* d;
   CK(cudaMalloc(&d, 148 * sizeof(long long)));
   size_t smem = 1024 + 16384 + 256 * 128;
-  CK(cudaFuncSetAttribute(umma_rate_kernel<N, TS, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  CK(cudaFuncSetAttribute(umma_rate_kernel<N, TS, KSTEPS, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   for (int rep = 0; rep < 2; ++rep) {
-    umma_rate_kernel<N, TS, KSTEPS><<<148, 128, smem>>>(d, iters, nacc);
+    umma_rate_kernel<N, TS, KSTEPS, LAYOUT><<<148, 128, smem>>>(d, iters, nacc);
     CK(cudaDeviceSynchronize());
   }
   std::vector<long long> h(148);
@@ -97,7 +109,7 @@ void run_rate(int nacc) {
     mn = std::min(mn, double(v));
   }
   const double per = mx / (double(iters) * KSTEPS);
-  printf("umma_rate M=128 N=%3d %s nacc=%d : %.2f cyc/MMA (ideal %.1f) -> %.1f%% of tensor peak  [min-cta %.2f]\n", N,
+  printf("umma_rate layout=%d M=128 N=%3d %s nacc=%d : %.2f cyc/MMA (ideal %.1f) -> %.1f%% of tensor peak  [min-cta %.2f]\n", LAYOUT, N,
          TS ? "TS" : "SS", nacc, per, N / 2.0, 100.0 * (N / 2.0) / per, mn / (double(iters) * KSTEPS));
   CK(cudaFree(d));
 }
@@ -311,21 +323,28 @@ int main(int argc, char** argv) {
     run_rate<32, false>(1); run_rate<32, false>(2); run_rate<64, false>(1); run_rate<64, false>(2);
     run_rate<96, false>(2); run_rate<128, false>(2); run_rate<256, false>(2);
     run_rate<32, true>(2); run_rate<64, true>(2); run_rate<128, true>(2);
+    run_rate<32, false, 1>(2); run_rate<32, false, 2>(2); run_rate<64, false, 1>(2); run_rate<64, false, 2>(2);
   }
   int good_mode[2] = {0, 0};  // per kc
   if (do_conv) {
-    for (int mode = 1; mode <= 3; ++mode) {
-      printf("tap_mode %d\n", mode);
+    for (int mode : {4, 1, 0}) {
+      printf("tap_mode %d (4 = column-scatter, 1 = haloed tap views, 0 = auto)\n", mode);
       // plain conv, interior + ragged borders, channel windows
       ConvCase a{2, 40, 24, 160, 32, 96, 32, 32, 160, 128, false, false, false, false, false, 1.0f};
       double ea = run_conv_case(a, mode, true);
       ConvCase b{1, 32, 16, 320, 64, 128, 64, 64, 320, 256, true, false, false, false, false, 0.2f};
       double eb = run_conv_case(b, mode, true);
-      if (ea < 2e-2 && !good_mode[0]) good_mode[0] = mode;
-      if (eb < 2e-2 && !good_mode[1]) good_mode[1] = mode;
+      (void)ea; (void)eb;
+      ConvCase c{3, 416, 416, 160, 0, 160, 32, 32, 160, 0, true, false, false, false, false, 0.2f};
+      if (mode == 4) run_conv_case(c, mode, true);  // full-size image: every CTA range starts/ends mid-strip
+      ConvCase d{2, 37, 50, 160, 32, 64, 32, 32, 160, 96, true, false, false, false, false, 0.2f};
+      run_conv_case(d, mode, true);  // ragged strip (37 = 4*8 + 5) and ragged last tile (50 = 3*16 + 2)
+      ConvCase s1{1, 8, 16, 160, 0, 32, 32, 32, 160, 32, true, false, false, false, false, 0.2f};
+      run_conv_case(s1, mode, true);  // exactly one tile: strip-end flush only
+      ConvCase s2{1, 5, 64, 160, 0, 96, 32, 32, 160, 96, true, false, false, false, false, 0.2f};
+      run_conv_case(s2, mode, true);  // one strip of 4 tiles on 4 CTAs: every range but the first has a pre-tile
     }
-    printf("first good tap_mode: kc32=%d kc64=%d\n", good_mode[0], good_mode[1]);
-    const int m32 = good_mode[0] ? good_mode[0] : 3, m64 = good_mode[1] ? good_mode[1] : 3;
+    const int m32 = 0, m64 = 0;
     // epilogue features
     ConvCase e1{2, 33, 19, 160, 0, 160, 32, 32, 32, 0, true, false, true, true, false, 1.0f};
     run_conv_case(e1, m32, true);
@@ -341,10 +360,9 @@ int main(int argc, char** argv) {
     good_mode[0] = good_mode[1] = 1;
   }
   if (do_time) {
-    for (int mode = 1; mode <= 3; ++mode) {
-      if (mode == 2) continue;
+    for (int mode : {4, 1}) {
       for (int k = 1; k <= 5; ++k) time_conv(16, 416, 416, 32, k, 32, mode);
-      time_conv(16, 416, 416, 32, 1, 32, mode, 128, true);
+      if (mode != 4) time_conv(16, 416, 416, 32, 1, 32, mode, 128, true);
       for (int k = 1; k <= 2; ++k) time_conv(8, 416, 416, 64, k, 64, mode);
     }
   }

@@ -22,6 +22,20 @@
 
 #include "ptx_sm100.cuh"
 
+#ifdef XMM_CONV_PROFILE
+#define XMM_PROF_T0() prof_t0_ = clock64()
+#define XMM_PROF_ADD(i) prof_acc_[i] += clock64() - prof_t0_
+#define XMM_PROF_START(i) long long prof_s_ = clock64()
+#define XMM_PROF_STOP(i) prof_acc_[i] += clock64() - prof_s_
+#define XMM_PROF_FLUSH(i) args.prof[size_t(blockIdx.x) * 8 + (i)] = prof_acc_[i]
+#else
+#define XMM_PROF_T0()
+#define XMM_PROF_ADD(i)
+#define XMM_PROF_START(i)
+#define XMM_PROF_STOP(i)
+#define XMM_PROF_FLUSH(i)
+#endif
+
 namespace xmm {
 
 constexpr int kTileH = 16;
@@ -66,6 +80,9 @@ struct ConvArgs {
   int tiles_x, tiles_y, num_tiles;
   int stages;
   ConvEpilogue epi;
+#ifdef XMM_CONV_PROFILE
+  long long* prof;  // [gridDim.x][8] cycle counters (tools/probe.cu only)
+#endif
 };
 
 template <int KC, int NT, int MODE>
@@ -115,22 +132,21 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
-// Epilogue for 32 accumulator columns [col0, col0+32) of one pixel.
-template <int NT>
-__device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const float* __restrict__ bias_s,
-                                                 uint32_t (&acc)[32], int col0, int b, int y, int x,
-                                                 int H, int W) {
-  float v[32];
+// Epilogue for NC accumulator columns [col0, col0+NC) of one pixel (NC = 16 or 32; acc holds raw fp32 sums).
+template <int NT, int NC>
+__device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const float* __restrict__ bias_s,
+                                                   float (&v)[NC], int col0, int b, int y, int x, int H, int W) {
+  static_assert(NC % 8 == 0, "whole 16-byte stores");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float t = __uint_as_float(acc[i]) + bias_s[col0 + i];
+  for (int i = 0; i < NC; ++i) {
+    const float t = v[i] + bias_s[col0 + i];
     v[i] = t > 0.f ? t : t * e.lrelu_slope;
   }
   const size_t pix = (size_t(b) * H + y) * W + x;
   if (e.mask != nullptr) {
     const uint4* mp = reinterpret_cast<const uint4*>(e.mask + pix * e.mask_ctot + e.mask_coff + col0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NC / 8; ++q) {
       float m[8];
       unpack8(__ldg(mp + q), m);
 #pragma unroll
@@ -138,11 +154,11 @@ __device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const fl
     }
   }
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] *= e.s0;
+  for (int i = 0; i < NC; ++i) v[i] *= e.s0;
   if (e.r1 != nullptr) {
     const uint4* rp = reinterpret_cast<const uint4*>(e.r1 + pix * e.r1_ctot + e.r1_coff + col0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NC / 8; ++q) {
       float m[8];
       unpack8(__ldg(rp + q), m);
 #pragma unroll
@@ -152,7 +168,7 @@ __device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const fl
   if (e.r2 != nullptr) {
     const uint4* rp = reinterpret_cast<const uint4*>(e.r2 + pix * e.r2_ctot + e.r2_coff + col0);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NC / 8; ++q) {
       float m[8];
       unpack8(__ldg(rp + q), m);
 #pragma unroll
@@ -173,7 +189,18 @@ __device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const fl
     op = reinterpret_cast<uint4*>(e.out + pix * e.out_ctot + e.out_coff + col0);
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q) op[q] = pack8(v + q * 8);
+  for (int q = 0; q < NC / 8; ++q) op[q] = pack8(v + q * 8);
+}
+
+// 32 raw accumulator registers (tcgen05.ld bit pattern) -> epilogue.
+template <int NT>
+__device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const float* __restrict__ bias_s,
+                                                 uint32_t (&acc)[32], int col0, int b, int y, int x,
+                                                 int H, int W) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  conv_epilogue_cols<NT, 32>(e, bias_s, v, col0, b, y, x, H, W);
 }
 
 template <int KC, int NT, int MODE>
@@ -195,6 +222,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef XMM_CONV_PROFILE
+  long long prof_t0_ = 0;
+  long long prof_acc_[6] = {0, 0, 0, 0, 0, 0};
+  const long long prof_k0_ = clock64();
+  unsigned long long prof_g0_;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_g0_));
+#endif
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_in);
@@ -236,7 +270,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
         const int tx = r - ty * args.tiles_x;
         const int y0 = ty * kTileH - 1, x0 = tx * kTileW - 1;
         for (int ch = 0; ch < args.nchunks; ++ch) {
+          XMM_PROF_T0();
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          XMM_PROF_ADD(0);
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageTx);
           uint8_t* dst = stage_s + size_t(stage) * Cfg::kStageBytes;
           const int c0 = args.cin_off + ch * KC;
@@ -249,6 +285,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
           }
         }
       }
+      XMM_PROF_FLUSH(0);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -263,12 +300,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      XMM_PROF_START(3);
       for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        XMM_PROF_T0();
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        XMM_PROF_ADD(1);
         ptx::tc_fence_after();
         const uint32_t d_addr = tmem_base + uint32_t(acc * NT);
         for (int ch = 0; ch < args.nchunks; ++ch) {
+          XMM_PROF_T0();
           ptx::mbar_wait(&full_bar[stage], phase);
+          XMM_PROF_ADD(2);
           ptx::tc_fence_after();
           const uint32_t a_stage = st_addr + uint32_t(stage) * Cfg::kStageBytes;
           const uint64_t bdesc_ch = bdesc0 + uint64_t((uint32_t(ch) * 9u * Cfg::kTapBytes) >> 4);
@@ -299,6 +341,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
+      XMM_PROF_STOP(3);
+      XMM_PROF_FLUSH(1); XMM_PROF_FLUSH(2); XMM_PROF_FLUSH(3);
     }
   } else {
     // ------------------------------------------------------------ epilogue
@@ -315,7 +359,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
       const int tx = r - ty * args.tiles_x;
       const int y = ty * kTileH + py, x = tx * kTileW + px;
       const bool valid = (y < args.height) && (x < args.width);
+      XMM_PROF_T0();
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      XMM_PROF_ADD(4);
+      XMM_PROF_T0();
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * NT);
 #pragma unroll 1
@@ -330,9 +377,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
         }
         if (valid) conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
       }
+      XMM_PROF_ADD(5);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (warp == 2 && lane == 0) { XMM_PROF_FLUSH(4); XMM_PROF_FLUSH(5); }
   }
 
   ptx::tc_fence_before();
@@ -341,6 +390,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+#ifdef XMM_CONV_PROFILE
+  if (threadIdx.x == 0) {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    args.prof[size_t(blockIdx.x) * 8 + 6] = clock64() - prof_k0_;
+    args.prof[size_t(blockIdx.x) * 8 + 7] = (long long)(g1 - prof_g0_);
+  }
+#endif
 }
 
 }  // namespace xmm

@@ -2,6 +2,7 @@
 // device properties and the cuTensorMapEncodeTiled entry point (resolved at run time so the
 // library links against libcudart only).
 #pragma once
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -117,9 +118,18 @@ inline int make_nhwc_tmap(CUtensorMap* out, const void* base, int batch, int hei
     sw = CU_TENSOR_MAP_SWIZZLE_64B;
   else if (box_c * 2 == 32)
     sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  // L2 promotion widens every TMA request to the given sector span.  The box's contiguous run is only
+  // box_c*2 bytes per pixel, so promoting past it over-fetches neighbouring channels from DRAM (measured
+  // 4x on 64-byte chunks with L2_256B).  XMM_TMAP_L2PROMO=0..3 overrides for experiments.
+  static const int promo_env = [] {
+    const char* e = getenv("XMM_TMAP_L2PROMO");
+    return e ? atoi(e) : -1;
+  }();
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (box_c * 2 <= 64) promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+  if (promo_env >= 0 && promo_env <= 3) promo = CUtensorMapL2promotion(promo_env);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(XMM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] box [%d,%d,%d]", int(r), batch,
                 height, width, ctot, box_c, box_w, box_h);

@@ -3,6 +3,7 @@
 
 #include <unordered_map>
 
+#include "conv3x3_dx.cuh"
 #include "conv3x3_tc.cuh"
 #include "edge_kernels.cuh"
 #include "host_common.cuh"
@@ -78,6 +79,17 @@ int cached_tmap(CUtensorMap* out, const void* base, int batch, int height, int w
   return XMM_OK;
 }
 
+void fill_epilogue(ConvEpilogue& e, const xmm_conv3x3_params& p) {
+  e.lrelu_slope = p.lrelu_slope;
+  e.mask_slope = p.mask_slope;
+  e.s0 = p.s0; e.s1 = p.s1; e.s2 = p.s2;
+  e.mask = static_cast<const __nv_bfloat16*>(p.mask); e.mask_ctot = p.mask_ctot; e.mask_coff = p.mask_coff;
+  e.r1 = static_cast<const __nv_bfloat16*>(p.r1); e.r1_ctot = p.r1_ctot; e.r1_coff = p.r1_coff;
+  e.r2 = static_cast<const __nv_bfloat16*>(p.r2); e.r2_ctot = p.r2_ctot; e.r2_coff = p.r2_coff;
+  e.out = static_cast<__nv_bfloat16*>(p.out); e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
+  e.pixel_shuffle = p.pixel_shuffle;
+}
+
 template <int KC, int NT, int MODE>
 int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
   using Cfg = ConvCfg<KC, NT, MODE>;
@@ -102,15 +114,7 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
   a.stages = stages;
   const size_t smem = Cfg::smem_bytes(a.w_bytes, stages);
 
-  ConvEpilogue& e = a.epi;
-  e.lrelu_slope = p.lrelu_slope;
-  e.mask_slope = p.mask_slope;
-  e.s0 = p.s0; e.s1 = p.s1; e.s2 = p.s2;
-  e.mask = static_cast<const __nv_bfloat16*>(p.mask); e.mask_ctot = p.mask_ctot; e.mask_coff = p.mask_coff;
-  e.r1 = static_cast<const __nv_bfloat16*>(p.r1); e.r1_ctot = p.r1_ctot; e.r1_coff = p.r1_coff;
-  e.r2 = static_cast<const __nv_bfloat16*>(p.r2); e.r2_ctot = p.r2_ctot; e.r2_coff = p.r2_coff;
-  e.out = static_cast<__nv_bfloat16*>(p.out); e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
-  e.pixel_shuffle = p.pixel_shuffle;
+  fill_epilogue(a.epi, p);
 
   CUtensorMap tmap;
   int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, Cfg::kPitchPx, kHaloH);
@@ -124,6 +128,46 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
   }
   const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
   conv3x3_tc_kernel<KC, NT, MODE><<<grid, kConvThreads, smem, stream>>>(tmap, a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+// Row-gather / column-scatter form (conv3x3_dx.cuh): the default for Cout = 32 / 64.
+template <int KC, int NT>
+int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  using Cfg = DxCfg<KC, NT>;
+  ConvArgs a{};
+  a.wblob = p.wblob;
+  a.nchunks = p.cin / KC;
+  a.w_bytes = uint32_t(a.nchunks) * 9u * Cfg::kTapBytes;
+  a.cin_off = p.in_coff;
+  a.batch = p.batch;
+  a.height = p.height;
+  a.width = p.width;
+  a.tiles_x = (p.width + kDxTileW - 1) / kDxTileW;
+  a.tiles_y = (p.height + kDxTileH - 1) / kDxTileH;
+  a.num_tiles = a.tiles_x * a.tiles_y * p.batch;
+  const size_t fixed = Cfg::smem_bytes(a.w_bytes, 0);
+  if (fixed + 2 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin))
+    return fail(XMM_ERR_UNSUPPORTED_SHAPE,
+                "conv3x3: weights of cin=%d cout=%d (%u B) do not fit in shared memory next to 2 pipeline stages",
+                p.cin, p.cout, a.w_bytes);
+  int stages = int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  a.stages = stages;
+  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages);
+  fill_epilogue(a.epi, p);
+  CUtensorMap tmap;
+  int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, kDxTileW, kDxPatchH);
+  if (rc != XMM_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dev.max_smem_optin));
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
+  conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
@@ -168,6 +212,17 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
                   (reinterpret_cast<uintptr_t>(p.wblob) & 15) == 0,
               "conv3x3: pointers must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // tap_mode 0 = auto: the column-scatter form (conv3x3_dx.cuh) wherever it is faster than the haloed tap views
+  // (measured on B200, 16x416x416: cin 64..160 -> 1.22x..1.49x; cin = 32 is epilogue-bound there).  4 forces it.
+  const bool dx_auto = p.tap_mode <= 0 && p.cin >= 2 * p.kc;
+  if (p.tap_mode == 4 || dx_auto) {
+    if (p.kc == 32 && p.cout == 32) return launch_conv_dx<32, 32>(p, dev, s);
+    if (p.kc == 64 && p.cout == 64 &&
+        (p.tap_mode == 4 || DxCfg<64, 64>::smem_bytes(uint32_t(p.cin / 64) * 9u * DxCfg<64, 64>::kTapBytes, 2) <=
+                                size_t(dev.max_smem_optin)))
+      return launch_conv_dx<64, 64>(p, dev, s);
+    XMM_REQUIRE(p.tap_mode != 4, "conv3x3: the column-scatter form is built for cout = kc = 32 or 64");
+  }
 #define XMM_CONV_CASE(KC_, NT_) \
   if (p.kc == KC_ && p.cout == NT_) return launch_conv_mode<KC_, NT_>(p, dev, s);
   XMM_CONV_CASE(32, 32)
