@@ -104,6 +104,18 @@ typedef struct {
 
 int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);
 
+/* A chain of dependent 3x3 convolutions -- the five convs of one ResidualDenseBlock_5C.forward
+ * (rrdb_blocks.py:37-54: each reads what the previous ones wrote) or the five data gradients of its backward --
+ * with the SAME result as calling xmm_conv3x3_bf16 on layers[0], layers[1], ... in order.
+ * mode 0: library chooses; 1: one pipelined launch (layer k runs on its own group of SMs two image strips behind
+ * layer k-1, so intermediate activations are consumed from L2; error if the layers do not qualify); 2: layer by
+ * layer.  Pipelining needs kc = cout = 32, one image geometry, no pixel shuffle, and no write-after-read between
+ * layers; masks / residuals must not be produced inside the chain.  `workspace` (device, borrowed for the call,
+ * xmm_conv3x3_chain_workspace_bytes) holds the strip-completion counters.                                      */
+size_t xmm_conv3x3_chain_workspace_bytes(int nlayers, int batch, int height);
+int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Input transforms ------------------------------------------------------------------- */
 #define XMM_STRETCH_LINEAR 0
 #define XMM_STRETCH_SQRT 1

@@ -314,10 +314,115 @@ static void time_conv(int B, int H, int W, int F, int k, int kc, int tap_mode, i
   cudaFree(in_d); if (out_d != in_d) cudaFree(out_d); cudaFree(w_d); cudaFree(blob); cudaFree(job_d);
 }
 
+// ------------------------------------------------------------------ dense-block chain: pipelined vs layer by layer
+// Forward dense block (rrdb_blocks.py:37-54): conv_k reads slots [0,k) of buf and writes slot k; conv5 writes slot 0
+// of `nxt` with the block residual.  Both runs use the column-scatter kernel (tap_mode 4), so the pipelined launch
+// must reproduce the layer-by-layer result BIT FOR BIT.
+static void run_chain_case(int B, int H, int W, bool time_it) {
+  const int F = 32, ctot = 5 * F;
+  std::mt19937 g(99);
+  const size_t npix = size_t(B) * H * W;
+  std::vector<__nv_bfloat16> buf_h(npix * ctot, __float2bfloat16_rn(-7.f));
+  {
+    std::uniform_real_distribution<float> d(-1.f, 1.f);
+    for (size_t p = 0; p < npix; ++p)
+      for (int c = 0; c < F; ++c) buf_h[p * ctot + c] = __float2bfloat16_rn(d(g));
+  }
+  __nv_bfloat16* buf_d[2] = {to_dev(buf_h), to_dev(buf_h)};
+  __nv_bfloat16* nxt_d[2];
+  for (int i = 0; i < 2; ++i) { CK(cudaMalloc(&nxt_d[i], npix * ctot * 2)); CK(cudaMemset(nxt_d[i], 0, npix * ctot * 2)); }
+  void* blobs[5];
+  std::vector<void*> frees;
+  for (int k = 1; k <= 5; ++k) {
+    const int cin = k * F;
+    std::vector<float> w_h(size_t(F) * cin * 9), b_h(F);
+    std::uniform_real_distribution<float> d(-0.06f, 0.06f);
+    for (auto& x : w_h) x = d(g);
+    for (auto& x : b_h) x = d(g);
+    float* w_d = to_dev(w_h);
+    float* b_d = to_dev(b_h);
+    CK(cudaMalloc(&blobs[k - 1], xmm_pack_blob_bytes(F, 32, cin / 32)));
+    xmm_pack_job job{};
+    job.dst = blobs[k - 1]; job.bias = b_d; job.nt = F; job.kc = 32; job.nchunks = cin / 32; job.nseg = 1;
+    job.n_valid = F; job.bias_n = F;
+    job.seg[0] = xmm_pack_segment{w_d, cin, 0, 0, 0, 0, cin, 1.0f, 0, F};
+    xmm_pack_job* job_d;
+    CK(cudaMalloc(&job_d, sizeof(job)));
+    CK(cudaMemcpy(job_d, &job, sizeof(job), cudaMemcpyHostToDevice));
+    if (xmm_pack_weights(job_d, 1, nullptr) != 0) { printf("pack failed: %s\n", xmm_last_error()); exit(2); }
+    frees.push_back(w_d); frees.push_back(b_d); frees.push_back(job_d);
+  }
+  auto make = [&](int which, xmm_conv3x3_params* L) {
+    for (int k = 1; k <= 5; ++k) {
+      xmm_conv3x3_params p{};
+      p.in = buf_d[which]; p.in_ctot = ctot; p.in_coff = 0; p.cin = k * F; p.wblob = blobs[k - 1]; p.kc = 32; p.cout = F;
+      p.batch = B; p.height = H; p.width = W; p.tap_mode = 4;
+      if (k < 5) {
+        p.lrelu_slope = 0.2f; p.s0 = 1.f; p.out = buf_d[which]; p.out_ctot = ctot; p.out_coff = k * F;
+      } else {
+        p.lrelu_slope = 1.f; p.s0 = 0.2f; p.r1 = buf_d[which]; p.r1_ctot = ctot; p.r1_coff = 0; p.s1 = 1.f;
+        p.out = nxt_d[which]; p.out_ctot = ctot; p.out_coff = 0;
+      }
+      L[k - 1] = p;
+    }
+  };
+  xmm_conv3x3_params La[5], Lb[5];
+  make(0, La);
+  make(1, Lb);
+  const size_t ws_bytes = xmm_conv3x3_chain_workspace_bytes(5, B, H);
+  void* ws;
+  CK(cudaMalloc(&ws, ws_bytes));
+  int rc = xmm_conv3x3_chain_bf16(La, 5, 2, ws, ws_bytes, nullptr);
+  if (rc) { printf("chain (layer by layer) failed: %s\n", xmm_last_error()); exit(2); }
+  rc = xmm_conv3x3_chain_bf16(Lb, 5, 1, ws, ws_bytes, nullptr);
+  if (rc) { printf("chain (pipelined) failed: %s\n", xmm_last_error()); exit(2); }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("chain kernel failed: %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<__nv_bfloat16> a(npix * ctot), b(npix * ctot), na(npix * ctot), nb(npix * ctot);
+  CK(cudaMemcpy(a.data(), buf_d[0], a.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), buf_d[1], b.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(na.data(), nxt_d[0], a.size() * 2, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(nb.data(), nxt_d[1], b.size() * 2, cudaMemcpyDeviceToHost));
+  size_t diff = 0, diff_n = 0, untouched = 0;
+  double amax = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    if (memcmp(&a[i], &b[i], 2) != 0) ++diff;
+    if (memcmp(&na[i], &nb[i], 2) != 0) ++diff_n;
+    if (__bfloat162float(b[i]) == -7.f) ++untouched;
+    amax = std::max(amax, double(std::fabs(__bfloat162float(nb[i]))));
+  }
+  printf("  chain B%d %dx%d: pipelined vs layer-by-layer: %zu / %zu differing values in the block buffer, %zu in the output (max |out| %.3g, unwritten %zu) %s\n",
+         B, H, W, diff, a.size(), diff_n, amax, untouched, (diff == 0 && diff_n == 0 && untouched == 0 && amax > 0) ? "OK" : "FAIL");
+  if (time_it) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int mode = 2; mode >= 1; --mode) {
+      float best = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        rc = xmm_conv3x3_chain_bf16(Lb, 5, mode, ws, ws_bytes, nullptr);
+        cudaEventRecord(e1);
+        if (rc) { printf("chain launch failed: %s\n", xmm_last_error()); break; }
+        CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best = std::min(best, ms);
+      }
+      const double flop = 2.0 * 9 * F * F * 15 * double(npix);
+      printf("  time chain B%d %dx%d mode=%d (%s): %.3f ms  %.1f TFLOP/s (%.1f%% of 1667.8)\n", B, H, W, mode,
+             mode == 1 ? "pipelined" : "layer by layer", best, flop / best * 1e-9, 100.0 * flop / best * 1e-9 / 1667.8);
+    }
+  }
+  for (int i = 0; i < 2; ++i) { cudaFree(buf_d[i]); cudaFree(nxt_d[i]); }
+  for (void* q : frees) cudaFree(q);
+  for (void* q : blobs) cudaFree(q);
+  cudaFree(ws);
+}
+
 int main(int argc, char** argv) {
   const bool do_rate = argc < 2 || strstr(argv[1], "rate");
   const bool do_conv = argc < 2 || strstr(argv[1], "conv");
   const bool do_time = argc < 2 || strstr(argv[1], "time");
+  const bool do_chain = argc < 2 || strstr(argv[1], "chain");
   if (xmm_check_device() != 0) { printf("device check failed: %s\n", xmm_last_error()); return 1; }
   if (do_rate) {
     run_rate<32, false>(1); run_rate<32, false>(2); run_rate<64, false>(1); run_rate<64, false>(2);
@@ -358,6 +463,16 @@ int main(int argc, char** argv) {
     run_conv_case(e5, m64, true);
   } else {
     good_mode[0] = good_mode[1] = 1;
+  }
+  if (argc >= 2 && strstr(argv[1], "sweep")) {  // timing only (env sweeps of XMM_CHAIN_SPLIT / XMM_CHAIN_SEGS)
+    run_chain_case(argc > 2 ? atoi(argv[2]) : 16, 416, 416, true);
+    return 0;
+  }
+  if (do_chain) {
+    run_chain_case(2, 40, 50, false);
+    run_chain_case(1, 8, 16, false);
+    run_chain_case(3, 100, 416, false);
+    run_chain_case(16, 416, 416, true);
   }
   if (do_time) {
     for (int mode : {4, 1}) {

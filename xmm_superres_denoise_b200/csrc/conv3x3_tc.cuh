@@ -132,14 +132,15 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return q;
 }
 
-// Epilogue for NC accumulator columns [col0, col0+NC) of one pixel (NC = 16 or 32; acc holds raw fp32 sums).
+// Fused epilogue arithmetic for NC accumulator columns [col0, col0+NC) of one pixel, in place on v (raw fp32 sums):
+// bias (bias_s == nullptr: already added), LeakyReLU, LeakyReLU' mask, scale, residuals.
 template <int NT, int NC>
-__device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const float* __restrict__ bias_s,
+__device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const float* __restrict__ bias_s,
                                                    float (&v)[NC], int col0, int b, int y, int x, int H, int W) {
-  static_assert(NC % 8 == 0, "whole 16-byte stores");
+  static_assert(NC % 8 == 0, "whole 16-byte accesses");
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    const float t = v[i] + bias_s[col0 + i];
+    const float t = bias_s != nullptr ? v[i] + bias_s[col0 + i] : v[i];
     v[i] = t > 0.f ? t : t * e.lrelu_slope;
   }
   const size_t pix = (size_t(b) * H + y) * W + x;
@@ -153,8 +154,10 @@ __device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const 
       for (int i = 0; i < 8; ++i) v[q * 8 + i] *= (m[i] > 0.f ? 1.f : e.mask_slope);
     }
   }
+  if (e.s0 != 1.f) {
 #pragma unroll
-  for (int i = 0; i < NC; ++i) v[i] *= e.s0;
+    for (int i = 0; i < NC; ++i) v[i] *= e.s0;
+  }
   if (e.r1 != nullptr) {
     const uint4* rp = reinterpret_cast<const uint4*>(e.r1 + pix * e.r1_ctot + e.r1_coff + col0);
 #pragma unroll
@@ -175,6 +178,14 @@ __device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const 
       for (int i = 0; i < 8; ++i) v[q * 8 + i] = fmaf(e.s2, m[i], v[q * 8 + i]);
     }
   }
+}
+
+// Epilogue for NC accumulator columns [col0, col0+NC) of one pixel: arithmetic + direct bf16 store.
+template <int NT, int NC>
+__device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const float* __restrict__ bias_s,
+                                                   float (&v)[NC], int col0, int b, int y, int x, int H, int W) {
+  conv_epilogue_math<NT, NC>(e, bias_s, v, col0, b, y, x, H, W);
+  const size_t pix = (size_t(b) * H + y) * W + x;
   uint4* op;
   if (e.pixel_shuffle == 2) {
     const int g = ((y & 1) << 1) | (x & 1);
@@ -188,6 +199,9 @@ __device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const 
   } else {
     op = reinterpret_cast<uint4*>(e.out + pix * e.out_ctot + e.out_coff + col0);
   }
+#ifdef XMM_EXP_NOSTORE
+  if (v[0] == 123.456f)
+#endif
 #pragma unroll
   for (int q = 0; q < NC / 8; ++q) op[q] = pack8(v + q * 8);
 }

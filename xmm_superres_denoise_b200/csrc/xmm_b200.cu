@@ -2,7 +2,9 @@
 #include "../../include/xmm_b200.h"
 
 #include <unordered_map>
+#include <vector>
 
+#include "conv3x3_chain.cuh"
 #include "conv3x3_dx.cuh"
 #include "conv3x3_tc.cuh"
 #include "edge_kernels.cuh"
@@ -160,6 +162,11 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   CUtensorMap tmap;
   int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, kDxTileW, kDxPatchH);
   if (rc != XMM_OK) return rc;
+  CUtensorMap tmap_out = tmap;  // unused (direct stores) when the output is pixel-shuffled
+  if (p.pixel_shuffle == 0) {
+    rc = cached_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, NT, kDxTileW, kDxTileH);
+    if (rc != XMM_OK) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -167,7 +174,7 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
     attr_set = true;
   }
   const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
-  conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, a);
+  conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
@@ -185,12 +192,8 @@ int launch_conv_mode(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStr
 
 }  // namespace
 
-extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
-  XMM_REQUIRE(pp != nullptr, "conv3x3: null params");
-  const xmm_conv3x3_params& p = *pp;
-  DeviceInfo dev;
-  int rc = require_sm100(&dev);
-  if (rc != XMM_OK) return rc;
+namespace {
+int check_conv_params(const xmm_conv3x3_params& p) {
   XMM_REQUIRE(p.in && p.out && p.wblob, "conv3x3: null tensor pointer");
   XMM_REQUIRE(p.batch > 0 && p.height > 0 && p.width > 0, "conv3x3: bad shape %dx%dx%d", p.batch, p.height, p.width);
   XMM_REQUIRE(p.kc == 32 || p.kc == 64, "conv3x3: kc must be 32 or 64 (got %d)", p.kc);
@@ -211,17 +214,27 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   XMM_REQUIRE((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(p.wblob) & 15) == 0,
               "conv3x3: pointers must be 16-byte aligned");
+  return XMM_OK;
+}
+}  // namespace
+
+extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "conv3x3: null params");
+  const xmm_conv3x3_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  rc = check_conv_params(p);
+  if (rc != XMM_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // tap_mode 0 = auto: the column-scatter form (conv3x3_dx.cuh) wherever it is faster than the haloed tap views
-  // (measured on B200, 16x416x416: cin 64..160 -> 1.22x..1.49x; cin = 32 is epilogue-bound there).  4 forces it.
-  const bool dx_auto = p.tap_mode <= 0 && p.cin >= 2 * p.kc;
+  // (measured on B200, 16x416x416, F=32: cin 64..160 -> 1.13x..1.37x; cin = 32 ties; F=64 layers are faster on the
+  // tap views, whose N=64 MMAs are less shared-memory bound).  4 forces it.
+  const bool dx_auto = p.tap_mode <= 0 && p.kc == 32 && p.cout == 32 && p.cin >= 64;
   if (p.tap_mode == 4 || dx_auto) {
     if (p.kc == 32 && p.cout == 32) return launch_conv_dx<32, 32>(p, dev, s);
-    if (p.kc == 64 && p.cout == 64 &&
-        (p.tap_mode == 4 || DxCfg<64, 64>::smem_bytes(uint32_t(p.cin / 64) * 9u * DxCfg<64, 64>::kTapBytes, 2) <=
-                                size_t(dev.max_smem_optin)))
-      return launch_conv_dx<64, 64>(p, dev, s);
-    XMM_REQUIRE(p.tap_mode != 4, "conv3x3: the column-scatter form is built for cout = kc = 32 or 64");
+    if (p.kc == 64 && p.cout == 64) return launch_conv_dx<64, 64>(p, dev, s);
+    return fail(XMM_ERR_INVALID_ARGUMENT, "conv3x3: the column-scatter form is built for cout = kc = 32 or 64");
   }
 #define XMM_CONV_CASE(KC_, NT_) \
   if (p.kc == KC_ && p.cout == NT_) return launch_conv_mode<KC_, NT_>(p, dev, s);
@@ -231,6 +244,207 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   XMM_CONV_CASE(64, 256)
 #undef XMM_CONV_CASE
   return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3: no kernel for kc=%d cout=%d", p.kc, p.cout);
+}
+
+// ----------------------------------------------------------------------------- conv chain (dense block)
+namespace {
+
+struct Window {
+  const void* base;
+  int ctot, c0, c1;
+};
+bool overlaps(const Window& a, const Window& b) {
+  return a.base && b.base && a.base == b.base && a.ctot == b.ctot && a.c0 < b.c1 && b.c0 < a.c1;
+}
+bool same(const Window& a, const Window& b) { return a.base == b.base && a.ctot == b.ctot && a.c0 == b.c0 && a.c1 == b.c1; }
+
+// Can layers[0..n) run as one pipelined launch?  (Same image geometry, the column-scatter kernel's layer shape,
+// and no hazard the strip-level dependency tracking does not cover.)
+const char* chain_blocker(const xmm_conv3x3_params* L, int n) {
+  if (n < 2 || n > kChainMaxLayers) return "2..5 layers";
+  for (int l = 0; l < n; ++l) {
+    const xmm_conv3x3_params& p = L[l];
+    if (p.kc != 32 || p.cout != 32) return "kc = cout = 32 layers only";
+    if (p.pixel_shuffle != 0) return "no pixel shuffle inside a chain";
+    if (p.batch != L[0].batch || p.height != L[0].height || p.width != L[0].width) return "one image geometry";
+    if (uint32_t(p.cin / 32) * 9u * DxCfg<32, 32>::kTapBytes > 160u * 1024u) return "weights must stay resident";
+  }
+  for (int l = 0; l < n; ++l) {
+    const Window in{L[l].in, L[l].in_ctot, L[l].in_coff, L[l].in_coff + L[l].cin};
+    const Window out{L[l].out, L[l].out_ctot, L[l].out_coff, L[l].out_coff + L[l].cout};
+    const Window side[3] = {{L[l].mask, L[l].mask_ctot, L[l].mask_coff, L[l].mask_coff + L[l].cout},
+                            {L[l].r1, L[l].r1_ctot, L[l].r1_coff, L[l].r1_coff + L[l].cout},
+                            {L[l].r2, L[l].r2_ctot, L[l].r2_coff, L[l].r2_coff + L[l].cout}};
+    if (overlaps(in, out)) return "a layer may not write its own input window";
+    for (int m = 0; m < n; ++m) {
+      const Window om{L[m].out, L[m].out_ctot, L[m].out_coff, L[m].out_coff + L[m].cout};
+      if (m > l && overlaps(in, om)) return "a later layer overwrites an earlier layer's input";
+      if (m != l && overlaps(out, om)) return "two layers write the same window";
+      for (const Window& sd : side) {
+        if (!sd.base) continue;
+        if (m == l ? (overlaps(sd, om) && !same(sd, om)) : overlaps(sd, om))
+          return "an epilogue input (mask / residual) is produced inside the chain";
+      }
+    }
+  }
+  return nullptr;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
+
+int launch_chain(const xmm_conv3x3_params* L, int n, const DeviceInfo& dev, int* done, cudaStream_t stream) {
+  using Cfg = DxCfg<32, 32>;
+  ChainArgs a{};
+  ChainTmaps tm{};
+  a.nlayers = n;
+  a.batch = L[0].batch;
+  a.height = L[0].height;
+  a.width = L[0].width;
+  a.tiles_x = (a.width + kDxTileW - 1) / kDxTileW;
+  a.tiles_y = (a.height + kDxTileH - 1) / kDxTileH;
+  int segs = env_int("XMM_CHAIN_SEGS", 2);
+  if (segs < 1) segs = 1;
+  if (segs > a.tiles_x) segs = a.tiles_x;
+  a.segs = segs;
+  a.done = done;
+  const int nstrips = a.batch * a.tiles_y;
+  const int grid = dev.sm_count;
+
+  // CTAs per layer in proportion to the layer's per-tile cost: 6 MMAs of 56 cycles per 32 input channels, but
+  // never less than the epilogue's three TMEM reads (48 KB at 64 B/clk).
+  double cost[kChainMaxLayers], total = 0;
+  for (int l = 0; l < n; ++l) {
+    const int nch = L[l].cin / 32;
+    cost[l] = 60.0 + 340.0 * nch;
+    if (cost[l] < 850.0) cost[l] = 850.0;
+    total += cost[l];
+  }
+  int cnt[kChainMaxLayers], used = 0;
+  for (int l = 0; l < n; ++l) {
+    cnt[l] = int(grid * cost[l] / total);
+    if (cnt[l] < 1) cnt[l] = 1;
+    used += cnt[l];
+  }
+  for (int l = n - 1; used < grid; l = (l + n - 1) % n) { ++cnt[l]; ++used; }   // leftovers to the heaviest layers
+  for (int l = 0; used > grid; l = (l + 1) % n) if (cnt[l] > 1) { --cnt[l]; --used; }
+  if (const char* e = getenv("XMM_CHAIN_SPLIT")) {  // "n0,n1,..." (experiments)
+    int v[kChainMaxLayers], k = 0, sum = 0;
+    for (const char* q = e; *q && k < n; ++k) {
+      v[k] = atoi(q);
+      sum += v[k];
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    if (k == n && sum <= grid) {
+      bool ok = true;
+      for (int l = 0; l < n; ++l) ok = ok && v[l] >= 1;
+      if (ok) for (int l = 0; l < n; ++l) cnt[l] = v[l];
+    }
+  }
+  size_t smem = 0;
+  int begin = 0;
+  for (int l = 0; l < n; ++l) {
+    ChainLayer& c = a.layer[l];
+    c.wblob = L[l].wblob;
+    c.nchunks = L[l].cin / 32;
+    c.w_bytes = uint32_t(c.nchunks) * 9u * Cfg::kTapBytes;
+    c.cin_off = L[l].in_coff;
+    c.cta_begin = begin;
+    c.cta_count = cnt[l];
+    begin += cnt[l];
+    const size_t fixed = Cfg::smem_bytes(c.w_bytes, 0);
+    int stages = int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    c.stages = stages;
+    const size_t need = Cfg::smem_bytes(c.w_bytes, stages);
+    if (need > smem) smem = need;
+    fill_epilogue(c.epi, L[l]);
+    int rc = cached_tmap(&tm.m[l], L[l].in, a.batch, a.height, a.width, L[l].in_ctot, 32, kDxTileW, kDxPatchH);
+    if (rc != XMM_OK) return rc;
+    rc = cached_tmap(&tm.out[l], L[l].out, a.batch, a.height, a.width, L[l].out_ctot, 32, kDxTileW, kDxTileH);
+    if (rc != XMM_OK) return rc;
+  }
+  const int total_ctas = begin;
+  XMM_CUDA_OK(cudaMemsetAsync(done, 0, size_t(n) * nstrips * sizeof(int), stream));
+  static bool attr_set = false;
+  if (!attr_set) {
+    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_chain_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     dev.max_smem_optin));
+    attr_set = true;
+  }
+  // XMM_CHAIN_PROF=1 (developer): per-layer-group cycle counters of this launch, printed after a device sync
+  static const bool prof_on = env_int("XMM_CHAIN_PROF", 0) != 0;
+  long long* prof_d = nullptr;
+  if (prof_on) {
+    XMM_CUDA_OK(cudaMalloc(&prof_d, size_t(total_ctas) * 4 * sizeof(long long)));
+    XMM_CUDA_OK(cudaMemsetAsync(prof_d, 0, size_t(total_ctas) * 4 * sizeof(long long), stream));
+    a.prof = prof_d;
+  }
+  void* kargs[2] = {&tm, &a};
+  // cooperative: every CTA must be resident, later layers spin on earlier layers' progress
+  XMM_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(conv3x3_chain_kernel<32, 32>), dim3(total_ctas),
+                                          dim3(kDxThreads), kargs, smem, stream));
+  if (prof_on) {
+    XMM_CUDA_OK(cudaStreamSynchronize(stream));
+    std::vector<long long> h(size_t(total_ctas) * 4);
+    XMM_CUDA_OK(cudaMemcpy(h.data(), prof_d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(prof_d);
+    for (int l = 0; l < n; ++l) {
+      double tot = 0, dep = 0, idle = 0, tiles = 0;
+      for (int c = a.layer[l].cta_begin; c < a.layer[l].cta_begin + a.layer[l].cta_count; ++c) {
+        tot += double(h[size_t(c) * 4]); dep += double(h[size_t(c) * 4 + 1]);
+        idle += double(h[size_t(c) * 4 + 2]); tiles += double(h[size_t(c) * 4 + 3]);
+      }
+      const double nc = a.layer[l].cta_count;
+      fprintf(stderr, "chain layer %d: %3d CTAs, nchunks %d, stages %d | per CTA: total %.0f cyc, dependency wait %.0f, "
+              "epilogue idle %.0f, tiles %.1f -> %.0f cyc/tile all-in, %.0f cyc/tile busy\n", l, a.layer[l].cta_count,
+              a.layer[l].nchunks, a.layer[l].stages, tot / nc, dep / nc, idle / nc, tiles / nc, tot / tiles,
+              (tot - idle) / tiles);
+    }
+  }
+  return XMM_OK;
+}
+
+}  // namespace
+
+extern "C" size_t xmm_conv3x3_chain_workspace_bytes(int nlayers, int batch, int height) {
+  if (nlayers < 1 || batch < 1 || height < 1) return 0;
+  return size_t(nlayers) * size_t(batch) * size_t((height + kDxTileH - 1) / kDxTileH) * sizeof(int);
+}
+
+extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  XMM_REQUIRE(layers != nullptr && nlayers >= 1, "conv3x3_chain: no layers");
+  XMM_REQUIRE(mode >= 0 && mode <= 2, "conv3x3_chain: mode must be 0 (auto), 1 (pipelined) or 2 (layer by layer)");
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  for (int l = 0; l < nlayers; ++l) {
+    rc = check_conv_params(layers[l]);
+    if (rc != XMM_OK) return rc;
+  }
+  const char* why = chain_blocker(layers, nlayers);
+  bool pipelined = mode != 2 && why == nullptr;
+  if (mode == 1 && why != nullptr) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3_chain: cannot pipeline (%s)", why);
+  if (pipelined) {
+    const size_t need = xmm_conv3x3_chain_workspace_bytes(nlayers, layers[0].batch, layers[0].height);
+    XMM_REQUIRE(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0,
+                "conv3x3_chain: workspace of %zu bytes needed (got %zu)", need, workspace_bytes);
+    if (mode == 0) {  // the pipeline needs a few waves of strip segments to fill
+      const long long strips = (long long)layers[0].batch * ((layers[0].height + kDxTileH - 1) / kDxTileH);
+      if (strips * 2 < 4LL * dev.sm_count) pipelined = false;
+    }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pipelined) return launch_chain(layers, nlayers, dev, static_cast<int*>(workspace), s);
+  for (int l = 0; l < nlayers; ++l) {
+    rc = xmm_conv3x3_bf16(&layers[l], stream);
+    if (rc != XMM_OK) return rc;
+  }
+  return XMM_OK;
 }
 
 // ----------------------------------------------------------------------------- transforms
