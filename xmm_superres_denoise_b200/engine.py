@@ -11,6 +11,7 @@ Owns what the reference leaves to autograd and cuDNN:
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -157,6 +158,9 @@ class RRDBEngine:
                 self.arena.add(_fwd_blob(f"f.up{s}", g.upsampling[3 * s], self.kc, perm=1))
             self.arena.add(_fwd_blob("f.hr", g.HRconv, self.kc))
         self._bufs: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        # how a dense block's five dependent convs are launched (ops.CHAIN_*): layer by layer is the measured
+        # optimum today; XMM_CHAIN_MODE=1 selects the pipelined single-launch kernel (F=32 only)
+        self.chain_mode = int(os.environ.get("XMM_CHAIN_MODE", ops.CHAIN_LAYER_BY_LAYER))
 
     @property
     def gen(self) -> nn.Module:
@@ -186,10 +190,10 @@ class RRDBEngine:
                      r2: Optional[torch.Tensor], s2: float) -> None:
         """One ResidualDenseBlock_5C (rrdb_blocks.py:37-54): x in buf[..., :F]; result -> out[..., :F]."""
         f, kc, a = self.nf, self.kc, self.arena
-        for k in range(1, 5):
-            ops.conv3x3(buf, 0, k * f, a.ptr(f"{name}.{k}"), kc, f, buf, k * f, lrelu=0.2)
-        ops.conv3x3(buf, 0, 5 * f, a.ptr(f"{name}.5"), kc, f, out, 0, s0=s0, r1=buf, r1_coff=0, s1=s1,
-                    r2=r2, r2_coff=0, s2=s2)
+        layers = [((buf, 0, k * f, a.ptr(f"{name}.{k}"), kc, f, buf, k * f), dict(lrelu=0.2)) for k in range(1, 5)]
+        layers.append(((buf, 0, 5 * f, a.ptr(f"{name}.5"), kc, f, out, 0),
+                       dict(s0=s0, r1=buf, r1_coff=0, s1=s1, r2=r2, r2_coff=0, s2=s2)))
+        ops.conv3x3_chain(layers, self.chain_mode)
 
     def _trunk_forward(self, x: torch.Tensor, rdb_bufs: List[torch.Tensor], fea: torch.Tensor,
                        trunk_out: torch.Tensor) -> None:

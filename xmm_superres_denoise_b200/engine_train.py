@@ -151,18 +151,21 @@ class TrainEngine(RRDBEngine):
         f, kc, a = self.nf, self.kc, self.arena
         act, ring = bufs["act"], bufs["ring"]
         A, G = act[3 * i + r], ring[r]
+        layers = []
         for j in range(4, 0, -1):  # dY_j = LeakyReLU'(x_j) * sum_k dgrad_k(dY_k)
-            ops.conv3x3(G, j * f, (5 - j) * f, a.ptr(f"d.{i}.{r}.{j}"), kc, f, G, (j - 1) * f, mask=A,
-                        mask_coff=j * f, mask_slope=0.2)
+            layers.append(((G, j * f, (5 - j) * f, a.ptr(f"d.{i}.{r}.{j}"), kc, f, G, (j - 1) * f),
+                           dict(mask=A, mask_coff=j * f, mask_slope=0.2)))
         # gradient of the block input: + skip connection(s)
         if r == 2:    # out_rrdb = 0.2 * out_rdb3 + x_rrdb ; G[4] holds E_i = dL/d(out_rrdb)
-            ops.conv3x3(G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[1], 4 * f, r1=G, r1_coff=4 * f, s1=0.2)
+            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[1], 4 * f), dict(r1=G, r1_coff=4 * f, s1=0.2))
         elif r == 1:
-            ops.conv3x3(G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[0], 4 * f, r1=G, r1_coff=4 * f, s1=1.0)
+            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[0], 4 * f), dict(r1=G, r1_coff=4 * f, s1=1.0))
         else:         # RDB1: + g_1 + E_i (RRDB skip); result is E_{i-1}, or dL/d(fea) through the trunk for i == 0
             out, ocoff = (ring[2], 4 * f) if i > 0 else (d_fea, 0)
-            ops.conv3x3(G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, out, ocoff, r1=G, r1_coff=4 * f, s1=1.0,
-                        r2=ring[2], r2_coff=4 * f, s2=1.0)
+            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, out, ocoff),
+                    dict(r1=G, r1_coff=4 * f, s1=1.0, r2=ring[2], r2_coff=4 * f, s2=1.0))
+        layers.append(last)
+        ops.conv3x3_chain(layers, self.chain_mode)
 
     def _rdb_wgrad(self, i: int, r: int, bufs, grads) -> None:
         f = self.nf

@@ -33,19 +33,15 @@ def _nhwc(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"{name}: expected [B,H,W,C], got {tuple(t.shape)}")
 
 
-def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, cout: int,
-            out: torch.Tensor, out_coff: int, *, lrelu: float = 1.0, s0: float = 1.0,
-            r1: Optional[torch.Tensor] = None, r1_coff: int = 0, s1: float = 0.0,
-            r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
-            mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
-            pixel_shuffle: int = 0, tap_mode: int = 0) -> None:
-    """out[..., out_coff:out_coff+cout] = epilogue(conv3x3(inp[..., in_coff:in_coff+cin])).
-
-    See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
+def _conv3x3_params(p: Conv3x3Params, inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, cout: int,
+                    out: torch.Tensor, out_coff: int, *, lrelu: float = 1.0, s0: float = 1.0,
+                    r1: Optional[torch.Tensor] = None, r1_coff: int = 0, s1: float = 0.0,
+                    r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
+                    mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
+                    pixel_shuffle: int = 0, tap_mode: int = 0) -> None:
     _nhwc(inp, "conv3x3 input")
     _nhwc(out, "conv3x3 output")
     b, h, w, ctot = inp.shape
-    p = Conv3x3Params()
     p.in_, p.in_ctot, p.in_coff, p.cin = inp.data_ptr(), ctot, in_coff, cin
     p.wblob, p.kc, p.cout = wblob_ptr, kc, cout
     p.batch, p.height, p.width = b, h, w
@@ -70,8 +66,42 @@ def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, 
     p.out, p.out_ctot, p.out_coff = out.data_ptr(), out.shape[3], out_coff
     p.pixel_shuffle = pixel_shuffle
     p.tap_mode = tap_mode
+
+
+def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, cout: int,
+            out: torch.Tensor, out_coff: int, **kw) -> None:
+    """out[..., out_coff:out_coff+cout] = epilogue(conv3x3(inp[..., in_coff:in_coff+cin])).
+
+    Keywords: lrelu, s0, r1/r1_coff/s1, r2/r2_coff/s2, mask/mask_coff/mask_slope, pixel_shuffle, tap_mode.
+    See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
+    p = Conv3x3Params()
+    _conv3x3_params(p, inp, in_coff, cin, wblob_ptr, kc, cout, out, out_coff, **kw)
     _lib.check(_lib.load().xmm_conv3x3_bf16(ctypes.byref(p), _lib.stream_ptr()))
     _count()
+
+
+CHAIN_AUTO, CHAIN_PIPELINED, CHAIN_LAYER_BY_LAYER = 0, 1, 2
+_chain_ws: dict = {}
+
+
+def conv3x3_chain(layers, mode: int = CHAIN_AUTO) -> None:
+    """Dependent 3x3 convolutions (one dense block: forward convs or backward data gradients) through
+    ``xmm_conv3x3_chain_bf16``.  ``layers``: list of (args, kwargs) exactly as for :func:`conv3x3`; the result equals
+    calling conv3x3 on them in order.  mode: CHAIN_AUTO / CHAIN_PIPELINED (one launch, layers pipelined over SM
+    groups) / CHAIN_LAYER_BY_LAYER."""
+    n = len(layers)
+    arr = (Conv3x3Params * n)()
+    for p, (a, kw) in zip(arr, layers):
+        _conv3x3_params(p, *a, **kw)
+    lib = _lib.load()
+    dev = layers[0][0][0].device
+    need = int(lib.xmm_conv3x3_chain_workspace_bytes(n, arr[0].batch, arr[0].height))
+    ws = _chain_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+        _chain_ws[dev] = ws
+    _lib.check(lib.xmm_conv3x3_chain_bf16(arr, n, int(mode), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    _count(1 if mode == CHAIN_PIPELINED else n)
 
 
 def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
