@@ -219,6 +219,16 @@ int xmm_conv3x3_wgrad(const xmm_wgrad_params* p, void* stream);
 int xmm_colsum_bf16(const void* in, int ctot, int c0, int n, size_t npix, float* out, float scale,
                     int accumulate, void* stream);
 
+/* Several channel windows of one buffer in a single pass (a dense block's five bias gradients).           */
+typedef struct {
+  int c0, n;          /* window [c0, c0+n), multiples of 8                                                */
+  float* out;         /* n floats                                                                         */
+  float scale;
+  int accumulate;     /* 0: out is zeroed first                                                           */
+} xmm_colsum_segment;
+int xmm_colsum_multi_bf16(const void* in, int ctot, size_t npix, const xmm_colsum_segment* segs, int nseg,
+                          void* stream);
+
 /* Weight/bias gradients of the two CUDA-core convolutions:
  *   R[o][c][tap] += sum_p s[o][p] * (V[p+off(tap)][c] + V2[p+off(tap)][c]);  S[o] += sum_p s[o][p]
  * conv_last: s = dL/dout (gated by the clamp), V = input features.  conv_first: s = input

@@ -109,7 +109,11 @@ class MsssimFinalizeParams(Structure):
                 ("gl_dev", c_void_p), ("weight", c_float)]
 
 
-EXTRA_STRUCTS = {"xmm_scale_stats": ScaleStats, "xmm_ssim_stats_params": SsimStatsParams,
+class ColsumSegment(Structure):
+    _fields_ = [("c0", c_int), ("n", c_int), ("out", c_void_p), ("scale", c_float), ("accumulate", c_int)]
+
+
+EXTRA_STRUCTS = {"xmm_colsum_segment": ColsumSegment, "xmm_scale_stats": ScaleStats, "xmm_ssim_stats_params": SsimStatsParams,
                  "xmm_ssim_grad_params": SsimGradParams, "xmm_msssim_finalize_params": MsssimFinalizeParams,
                  "xmm_wgrad_role": WgradRole, "xmm_wgrad_dst": WgradDst, "xmm_wgrad_params": WgradParams,
                  "xmm_edge_wgrad_params": EdgeWgradParams}
@@ -133,6 +137,7 @@ SIGNATURES = {
     "xmm_wgrad_workspace_bytes": (c_size_t, []),
     "xmm_conv3x3_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "xmm_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_float, c_int, c_void_p]),
+    "xmm_colsum_multi_bf16": (c_int, [c_void_p, c_int, c_size_t, POINTER(ColsumSegment), c_int, c_void_p]),
     "xmm_edge_wgrad": (c_int, [POINTER(EdgeWgradParams), c_void_p]),
     "xmm_loss_workspace_floats": (c_size_t, []),
     "xmm_loss_reduce": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -276,7 +276,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // with s an fp32 NCHW image (optionally gated by the forward clamp) and V a bf16 NHWC window.
 //   conv_last:  s = dL/d(out), V = its input features          -> dW[o][c][tap] = R, db[o] = S
 //   conv_first: s = the input image x, V = dL/d(fea)           -> dW[f][o][8-tap] = R[o][f][tap]
-// Block = C x 9 threads (one per (channel, tap)); each block walks a strip of pixels.
+// One CTA (256 threads) owns `rows` image rows of one image.  The (gated) s rows, with a one-pixel zero halo, are
+// staged in shared memory; V is then streamed ONCE, 16 bytes (8 channels) per thread and pixel, and every thread
+// keeps an 8-channel x 9-tap accumulator block in registers: R[c][tap] += s[q - off(tap)] * V[q][c].  Warp
+// shuffles, a shared-memory pass and one atomicAdd per (channel, tap) and CTA finish the sum.
+// HBM-bound: C*2 (+C*2) + 4 (+4) bytes per pixel.
 struct EdgeWgradArgs {
   const float* s;     // [B][ns][H][W]
   const float* gate;  // optional clamp gate for s
@@ -285,47 +289,100 @@ struct EdgeWgradArgs {
   float* r;           // [ns][C][9]
   float* ssum;        // [ns] or nullptr
   int batch, ns, height, width;
-  int pixels_per_block;
+  int rows;           // image rows per CTA
 };
 
+constexpr int kEdgeWgradThreads = 256;
+
 template <int C>
-__global__ void __launch_bounds__(C * 9) edge_wgrad_kernel(const EdgeWgradArgs a) {
-  const int c = threadIdx.x % C, tap = threadIdx.x / C;
-  const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-  const size_t hw = size_t(a.height) * a.width;
-  const size_t npix = hw * a.batch;
-  const size_t p0 = size_t(blockIdx.x) * a.pixels_per_block;
-  const size_t p1 = p0 + a.pixels_per_block < npix ? p0 + a.pixels_per_block : npix;
-  const int b0 = int(p0 / hw);
-  const int rem0 = int(p0 - size_t(b0) * hw);
+__global__ void __launch_bounds__(kEdgeWgradThreads) edge_wgrad_kernel(const EdgeWgradArgs a) {
+  constexpr int LP = C / 8;                       // lanes per pixel
+  constexpr int PPI = kEdgeWgradThreads / LP;     // pixels per CTA iteration
+  extern __shared__ float sm[];
+  const int W = a.width, H = a.height;
+  const int pitch = W + 2;
+  float* s_tile = sm;                                        // [rows + 2][W + 2]
+  float* red = sm + size_t(a.rows + 2) * pitch;              // [8 warps][C * 9]
+  __shared__ float ssum_s;
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * a.rows;
+  const int nrows = (y0 + a.rows <= H) ? a.rows : H - y0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = tid / LP, cg = tid % LP;
+  const size_t hw = size_t(H) * W;
+
   for (int o = 0; o < a.ns; ++o) {
-    float acc = 0.0f, ss = 0.0f;
-    int b = b0, y = rem0 / a.width, x = rem0 - (rem0 / a.width) * a.width;
-    for (size_t p = p0; p < p1; ++p) {
-      const size_t si = (size_t(b) * a.ns + o) * hw + size_t(y) * a.width + x;
-      float sv = __ldg(a.s + si);
-      if (a.gate != nullptr) {
-        const float gt = __ldg(a.gate + si);
-        if (!(gt >= 0.0f && gt <= 1.0f)) sv = 0.0f;
-      }
-      ss += sv;
-      const int yy = y + dy, xx = x + dx;
-      if (sv != 0.0f && yy >= 0 && yy < a.height && xx >= 0 && xx < a.width) {
-        const size_t q = (size_t(b) * a.height + yy) * a.width + xx;
-        float vv = __bfloat162float(a.v[q * a.v_ctot + a.v_coff + c]);
-        if (a.v2 != nullptr) vv += __bfloat162float(a.v2[q * a.v2_ctot + a.v2_coff + c]);
-        acc = fmaf(sv, vv, acc);
-      }
-      if (++x == a.width) {
-        x = 0;
-        if (++y == a.height) {
-          y = 0;
-          ++b;
+    if (tid == 0) ssum_s = 0.f;
+    __syncthreads();  // previous plane's readers are done with s_tile / red
+    // ---- stage s rows y0-1 .. y0+rows with a zero halo; sum the owned rows
+    const float* sp = a.s + (size_t(b) * a.ns + o) * hw;
+    const float* gp = a.gate != nullptr ? a.gate + (size_t(b) * a.ns + o) * hw : nullptr;
+    float ss = 0.f;
+    for (int i = tid; i < (a.rows + 2) * pitch; i += kEdgeWgradThreads) {
+      const int r = i / pitch, cx = i - r * pitch;
+      const int y = y0 - 1 + r, x = cx - 1;
+      float sv = 0.f;
+      if (y >= 0 && y < H && x >= 0 && x < W) {
+        sv = __ldg(sp + size_t(y) * W + x);
+        if (gp != nullptr) {
+          const float gt = __ldg(gp + size_t(y) * W + x);
+          if (!(gt >= 0.0f && gt <= 1.0f)) sv = 0.0f;
         }
+        if (r >= 1 && r <= nrows) ss += sv;
+      }
+      s_tile[i] = sv;
+    }
+    if (a.ssum != nullptr) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+      if (lane == 0) atomicAdd(&ssum_s, ss);
+    }
+    __syncthreads();
+    // ---- stream V
+    float acc[8][9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[i][t] = 0.f;
+    const int npx = nrows * W;
+    for (int idx = slot; idx < npx; idx += PPI) {
+      const int y = idx / W, x = idx - y * W;
+      const size_t q = (size_t(b) * H + (y0 + y)) * W + x;
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a.v + q * a.v_ctot + a.v_coff + cg * 8)), v);
+      if (a.v2 != nullptr) {
+        float w2[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.v2 + q * a.v2_ctot + a.v2_coff + cg * 8)), w2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += w2[i];
+      }
+      const float* st = s_tile + (y + 1) * pitch + (x + 1);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const float sv = st[-dy * pitch - dx];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][t] = fmaf(sv, v[i], acc[i][t]);
       }
     }
-    atomicAdd(a.r + (size_t(o) * C + c) * 9 + tap, acc);
-    if (a.ssum != nullptr && threadIdx.x == 0) atomicAdd(a.ssum + o, ss);
+    // ---- reduce: lanes of a warp with the same channel group, then the 8 warps, then one atomic per value
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float x = acc[i][t];
+#pragma unroll
+        for (int d = LP; d < 32; d <<= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane < LP) red[warp * (C * 9) + (cg * 8 + i) * 9 + t] = x;
+      }
+    __syncthreads();
+    for (int i = tid; i < C * 9; i += kEdgeWgradThreads) {
+      float x = 0.f;
+#pragma unroll
+      for (int w = 0; w < kEdgeWgradThreads / 32; ++w) x += red[w * (C * 9) + i];
+      atomicAdd(a.r + size_t(o) * C * 9 + i, x);
+    }
+    if (a.ssum != nullptr && tid == 0) atomicAdd(a.ssum + o, ssum_s);
   }
 }
 

@@ -213,31 +213,70 @@ __global__ void wgrad_reduce_kernel(const WgradReduceArgs a, int num_tiles) {
   }
 }
 
-// Column sums of a bf16 NHWC channel window: bias gradients  db[n] = scale * sum_p dY[p][c0 + n].
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ in, int ctot, int c0, int n, size_t npix,
-                              float* __restrict__ out, float scale) {
-  // blockDim.x = 256 threads: thread -> (pixel lane = tid / n8, channel group = tid % n8), n8 = n / 8
-  extern __shared__ float red[];
-  const int n8 = n / 8;
-  const int ppb = blockDim.x / n8;  // pixels per block iteration
-  const int cg = threadIdx.x % n8, pl = threadIdx.x / n8;
+// Column sums of bf16 NHWC channel windows: bias gradients  db[n] = scale * sum_p dY[p][c0 + n], for up to
+// kColsumMaxSeg windows of one buffer in ONE pass (a dense block's five bias gradients are five windows of its
+// gradient buffer).  Thread -> (pixel lane, 8-channel group); 4 independent 16-byte loads in flight per thread.
+constexpr int kColsumMaxSeg = 8;
+constexpr int kColsumThreads = 256;
+struct ColsumSeg {
+  int c0, n, group0;
+  float scale;
+  float* out;
+};
+struct ColsumArgs {
+  const __nv_bfloat16* in;
+  int ctot, nseg, ngroups;
+  size_t npix;
+  ColsumSeg seg[kColsumMaxSeg];
+};
+
+__global__ void __launch_bounds__(kColsumThreads) colsum_multi_kernel(const ColsumArgs a) {
+  __shared__ float red[kColsumThreads * 8];
+  const int ppb = kColsumThreads / a.ngroups;  // pixel lanes per block
+  const int g = threadIdx.x % a.ngroups, pl = threadIdx.x / a.ngroups;
+  int si = 0;
+#pragma unroll
+  for (int i = 1; i < kColsumMaxSeg; ++i)
+    if (i < a.nseg && g >= a.seg[i].group0) si = i;
+  const int ch = a.seg[si].c0 + (g - a.seg[si].group0) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (pl < ppb) {
-    for (size_t p = size_t(blockIdx.x) * ppb + pl; p < npix; p += size_t(gridDim.x) * ppb) {
+    const size_t stride = size_t(gridDim.x) * ppb;
+    size_t p = size_t(blockIdx.x) * ppb + pl;
+    const __nv_bfloat16* base = a.in + ch;
+    for (; p + 3 * stride < a.npix; p += 4 * stride) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(base + (p + u * stride) * a.ctot));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+    }
+    for (; p < a.npix; p += stride) {
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(in + p * ctot + c0 + cg * 8)), v);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + p * a.ctot)), v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  if (pl < ppb) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&red[cg * 8 + i], acc[i]);
-  }
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = (pl < ppb) ? acc[i] : 0.f;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&out[i], scale * red[i]);
+  // thread t < ngroups * 8: channel t of the concatenated windows; sum over the pixel lanes
+  for (int t = threadIdx.x; t < a.ngroups * 8; t += kColsumThreads) {
+    const int gg = t / 8, i = t % 8;
+    float x = 0.f;
+    for (int l = 0; l < ppb; ++l) x += red[(l * a.ngroups + gg) * 8 + i];
+    int sj = 0;
+#pragma unroll
+    for (int k = 1; k < kColsumMaxSeg; ++k)
+      if (k < a.nseg && gg >= a.seg[k].group0) sj = k;
+    atomicAdd(a.seg[sj].out + (gg - a.seg[sj].group0) * 8 + i, a.seg[sj].scale * x);
+  }
 }
 
 }  // namespace xmm

@@ -668,21 +668,45 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   return XMM_OK;
 }
 
-extern "C" int xmm_colsum_bf16(const void* in, int ctot, int c0, int n, size_t npix, float* out, float scale,
-                               int accumulate, void* stream) {
+extern "C" int xmm_colsum_multi_bf16(const void* in, int ctot, size_t npix, const xmm_colsum_segment* segs, int nseg,
+                                     void* stream) {
   DeviceInfo dev;
   int rc = require_sm100(&dev);
   if (rc != XMM_OK) return rc;
-  XMM_REQUIRE(in && out, "colsum: null tensor pointer");
-  XMM_REQUIRE(n > 0 && n % 8 == 0 && n <= 256 && c0 % 8 == 0 && ctot % 8 == 0 && c0 + n <= ctot,
-              "colsum: channel window [%d,%d) of %d", c0, c0 + n, ctot);
+  XMM_REQUIRE(in && segs && nseg >= 1 && nseg <= kColsumMaxSeg, "colsum: 1..%d segments", kColsumMaxSeg);
+  XMM_REQUIRE(ctot % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "colsum: input alignment");
+  ColsumArgs a{};
+  a.in = static_cast<const __nv_bfloat16*>(in);
+  a.ctot = ctot;
+  a.npix = npix;
+  a.nseg = nseg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!accumulate) XMM_CUDA_OK(cudaMemsetAsync(out, 0, size_t(n) * sizeof(float), s));
+  int groups = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const xmm_colsum_segment& g = segs[i];
+    XMM_REQUIRE(g.out != nullptr && g.n > 0 && g.n % 8 == 0 && g.c0 % 8 == 0 && g.c0 >= 0 && g.c0 + g.n <= ctot,
+                "colsum: channel window [%d,%d) of %d", g.c0, g.c0 + g.n, ctot);
+    a.seg[i].c0 = g.c0; a.seg[i].n = g.n; a.seg[i].out = g.out; a.seg[i].scale = g.scale;
+    a.seg[i].group0 = groups;
+    groups += g.n / 8;
+    if (!g.accumulate) XMM_CUDA_OK(cudaMemsetAsync(g.out, 0, size_t(g.n) * sizeof(float), s));
+  }
+  XMM_REQUIRE(groups <= kColsumThreads, "colsum: %d channels in one call (max %d)", groups * 8, kColsumThreads * 8);
+  a.ngroups = groups;
   if (npix == 0) return XMM_OK;
-  colsum_kernel<<<dev.sm_count * 8, 256, size_t(n) * sizeof(float), s>>>(static_cast<const __nv_bfloat16*>(in), ctot,
-                                                                        c0, n, npix, out, scale);
+  const int ppb = kColsumThreads / groups;
+  size_t want = (npix + size_t(ppb) * 8 - 1) / (size_t(ppb) * 8);  // >= 8 pixels per thread
+  const size_t cap = size_t(dev.sm_count) * 8;
+  const unsigned grid = unsigned(want < 1 ? 1 : (want > cap ? cap : want));
+  colsum_multi_kernel<<<grid, kColsumThreads, 0, s>>>(a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
+}
+
+extern "C" int xmm_colsum_bf16(const void* in, int ctot, int c0, int n, size_t npix, float* out, float scale,
+                               int accumulate, void* stream) {
+  xmm_colsum_segment g{c0, n, out, scale, accumulate};
+  return xmm_colsum_multi_bf16(in, ctot, npix, &g, 1, stream);
 }
 
 extern "C" int xmm_edge_wgrad(const xmm_edge_wgrad_params* pp, void* stream) {
@@ -698,15 +722,34 @@ extern "C" int xmm_edge_wgrad(const xmm_edge_wgrad_params* pp, void* stream) {
   a.v = static_cast<const __nv_bfloat16*>(p.v); a.v_ctot = p.v_ctot; a.v_coff = p.v_coff;
   a.v2 = static_cast<const __nv_bfloat16*>(p.v2); a.v2_ctot = p.v2_ctot; a.v2_coff = p.v2_coff;
   a.r = p.r; a.ssum = p.ssum; a.batch = p.batch; a.ns = p.ns; a.height = p.height; a.width = p.width;
-  const size_t npix = size_t(p.batch) * p.height * p.width;
-  int ppb = int((npix + size_t(dev.sm_count) * 16 - 1) / (size_t(dev.sm_count) * 16));
-  if (ppb < 64) ppb = 64;
-  a.pixels_per_block = ppb;
-  const unsigned grid = unsigned((npix + ppb - 1) / ppb);
+  XMM_REQUIRE(p.v_ctot % 8 == 0 && p.v_coff % 8 == 0 && (!p.v2 || (p.v2_ctot % 8 == 0 && p.v2_coff % 8 == 0)),
+              "edge_wgrad: channel windows must be 8-channel aligned");
+  XMM_REQUIRE(p.channels == 32 || p.channels == 64, "edge_wgrad: channels=%d (supported: 32, 64)", p.channels);
+  // rows per CTA: as many as fit 40 KB of staged s rows (+ halo), at most 8
+  const size_t red_bytes = size_t(kEdgeWgradThreads / 32) * p.channels * 9 * sizeof(float);
+  int rows = int((40 * 1024) / (size_t(p.width + 2) * sizeof(float))) - 2;
+  if (rows > 8) rows = 8;
+  if (rows > p.height) rows = p.height;
+  XMM_REQUIRE(rows >= 1, "edge_wgrad: image width %d too large for the shared-memory row staging", p.width);
+  a.rows = rows;
+  const size_t smem = size_t(rows + 2) * (p.width + 2) * sizeof(float) + red_bytes;
+  const dim3 grid(unsigned((p.height + rows - 1) / rows), unsigned(p.batch));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p.channels == 32) edge_wgrad_kernel<32><<<grid, 32 * 9, 0, s>>>(a);
-  else if (p.channels == 64) edge_wgrad_kernel<64><<<grid, 64 * 9, 0, s>>>(a);
-  else return fail(XMM_ERR_UNSUPPORTED_SHAPE, "edge_wgrad: channels=%d (supported: 32, 64)", p.channels);
+  if (p.channels == 32) {
+    static bool attr32 = false;
+    if (!attr32) {
+      XMM_CUDA_OK(cudaFuncSetAttribute(edge_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr32 = true;
+    }
+    edge_wgrad_kernel<32><<<grid, kEdgeWgradThreads, smem, s>>>(a);
+  } else {
+    static bool attr64 = false;
+    if (!attr64) {
+      XMM_CUDA_OK(cudaFuncSetAttribute(edge_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr64 = true;
+    }
+    edge_wgrad_kernel<64><<<grid, kEdgeWgradThreads, smem, s>>>(a);
+  }
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }

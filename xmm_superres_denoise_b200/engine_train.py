@@ -145,7 +145,7 @@ class TrainEngine(RRDBEngine):
                 ops.colsum(dy, 0, n, tmp)
                 db.copy_(tmp.view(4, n // 4).t().reshape(n))  # packed g*F+c -> channel 4c+g
             else:
-                ops.colsum(dy, 0, n, db)
+                ops.colsum(dy, 0, n, db, accumulate=True)  # db is a view of the zero-initialised flat buffer
 
     def _rdb_backward(self, i: int, r: int, bufs, grads, d_fea: torch.Tensor) -> None:
         f, kc, a = self.nf, self.kc, self.arena
@@ -174,7 +174,7 @@ class TrainEngine(RRDBEngine):
         A, G = bufs["act"][3 * i + r], bufs["ring"][r]
         s5 = 0.04 if r == 2 else 0.2
         roles = [(3 * d, 3, 0, 2, 0, 5 * f) for d in range(3)] + [(0, 9, 4 * f, 1, 4 * f, f)]
-        dsts = []
+        dsts, bias_segs = [], []
         for k in range(1, 6):
             conv = getattr(rdb, f"conv{k}")
             dw = self._gv(grads, conv.weight)
@@ -183,8 +183,10 @@ class TrainEngine(RRDBEngine):
                 dsts.append((dw, f, k * f, 0, min(k * f, 4 * f), d, 0, (k - 1) * f, sc, 0, 0))
             if k == 5:
                 dsts.append((dw, f, 5 * f, 4 * f, 5 * f, 3, 0, 0, sc, 0, 0))
-            if conv.bias is not None:
-                ops.colsum(G, (k - 1) * f, f, self._gv(grads, conv.bias), scale=sc)
+            if conv.bias is not None:  # accumulate: the flat gradient buffer starts at zero
+                bias_segs.append(((k - 1) * f, f, self._gv(grads, conv.bias), sc, True))
+        if bias_segs:
+            ops.colsum_multi(G, bias_segs)  # the five bias gradients: one pass over the block's gradient buffer
         ops.conv3x3_wgrad(A, G, roles, dsts)
 
     def backward(self, bufs, generation: int, x: torch.Tensor, gout: torch.Tensor, need_x_grad: bool,

@@ -261,6 +261,19 @@ def colsum(inp: torch.Tensor, c0: int, n: int, out: torch.Tensor, scale: float =
     _count()
 
 
+def colsum_multi(inp: torch.Tensor, segments) -> None:
+    """Several bias gradients in one pass over ``inp``.  segments: [(c0, n, out, scale, accumulate)]."""
+    _nhwc(inp, "colsum input")
+    arr = (_lib.ColsumSegment * len(segments))()
+    for a, (c0, n, out, scale, accumulate) in zip(arr, segments):
+        _lib.require_cuda_tensor(out, torch.float32, "colsum output")
+        a.c0, a.n, a.out, a.scale, a.accumulate = c0, n, out.data_ptr(), scale, int(accumulate)
+    npix = inp.shape[0] * inp.shape[1] * inp.shape[2]
+    _lib.check(_lib.load().xmm_colsum_multi_bf16(inp.data_ptr(), inp.shape[3], npix, arr, len(segments),
+                                                 _lib.stream_ptr()))
+    _count()
+
+
 def edge_wgrad(s: torch.Tensor, v: torch.Tensor, v_coff: int, channels: int, r: torch.Tensor,
                ssum: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
                v2: Optional[torch.Tensor] = None, v2_coff: int = 0) -> None:
