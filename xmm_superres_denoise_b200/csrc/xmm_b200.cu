@@ -230,7 +230,9 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   // tap_mode 0 = auto: the column-scatter form (conv3x3_dx.cuh) wherever it is faster than the haloed tap views
   // (measured on B200, 16x416x416, F=32: cin 64..160 -> 1.13x..1.37x; cin = 32 ties; F=64 layers are faster on the
   // tap views, whose N=64 MMAs are less shared-memory bound).  4 forces it.
-  const bool dx_auto = p.tap_mode <= 0 && p.kc == 32 && p.cout == 32 && p.cin >= 64;
+  const bool dx_auto = p.tap_mode <= 0 && p.kc == 32 && p.cout == 32 && p.cin >= 64 &&
+                       DxCfg<32, 32>::smem_bytes(uint32_t(p.cin / 32) * 9u * DxCfg<32, 32>::kTapBytes, 4) <=
+                           size_t(dev.max_smem_optin);  // >= 4 pipeline stages next to the resident weights
   if (p.tap_mode == 4 || dx_auto) {
     if (p.kc == 32 && p.cout == 32) return launch_conv_dx<32, 32>(p, dev, s);
     if (p.kc == 64 && p.cout == 64) return launch_conv_dx<64, 64>(p, dev, s);

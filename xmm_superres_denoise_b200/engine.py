@@ -133,7 +133,54 @@ def _fwd_blob(name: str, conv: nn.Conv2d, kc: int, perm: int = 0) -> _Blob:
                  [_Segment(conv.weight, cin, 0, 0, 0, 0, cin, 1.0)], conv.bias, perm)
 
 
-class RRDBEngine:
+class _LayerPlans:
+    """Mixin: packed forward layers of an engine (``self.arena``, ``self.plans``, ``self.kc``)."""
+
+    def _add_forward_layer(self, name: str, conv: nn.Conv2d, perm: int = 0) -> None:
+        """Packed weights of one forward conv.  The kernels keep a layer's weights resident in shared memory; a
+        layer that does not fit (F=64: 9*cin*cout*2 bytes reaches 368 KB) is split along its OUTPUT channels into
+        parts of 32 (128 for the pixel-shuffle conv) packed with 32-channel K chunks, and runs as one launch per
+        part into adjacent output windows."""
+        cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+        if 9 * cin * cout * 2 <= _WEIGHT_BUDGET:
+            self.arena.add(_fwd_blob(name, conv, self.kc, perm))
+            self.plans[name] = [(name, self.kc, cout, 0)]
+            return
+        part = 128 if perm else 32
+        if cout % part or 9 * cin * part * 2 > 190 * 1024:
+            raise NotImplementedError(f"{name}: a {cin}->{cout} conv does not fit the resident-weight kernels")
+        plan = []
+        for n0 in range(0, cout, part):
+            pname = f"{name}.n{n0}"
+            self.arena.add(_Blob(pname, part, 32, cin // 32, [_Segment(conv.weight, cin, n0, 0, 0, 0, cin, 1.0)],
+                                 conv.bias, perm))
+            plan.append((pname, 32, part, n0))
+        self.plans[name] = plan
+
+    def _conv(self, name: str, inp: torch.Tensor, in_coff: int, cin: int, out: torch.Tensor, out_coff: int, **kw):
+        """The launches of one planned layer as (args, kwargs) for ops.conv3x3 / ops.conv3x3_chain."""
+        calls = []
+        shuffle = kw.get("pixel_shuffle", 0) == 1
+        for blob, kc, nt, n0 in self.plans[name]:
+            k2 = dict(kw)
+            for key in ("r1_coff", "r2_coff", "mask_coff"):
+                if key in k2 and k2.get(key[:-5]) is not None:
+                    k2[key] = k2[key] + n0
+            calls.append(((inp, in_coff, cin, self.arena.ptr(blob), kc, nt, out, out_coff + (n0 // 4 if shuffle else n0)),
+                          k2))
+        return calls
+
+    def _run(self, calls) -> None:
+        for a, kw in calls:
+            ops.conv3x3(*a, **kw)
+
+
+
+# Shared memory a conv CTA can spend on resident weights and still keep >= 2 activation stages (227 KB opt-in).
+_WEIGHT_BUDGET = 150 * 1024
+
+
+class RRDBEngine(_LayerPlans):
     """Forward pass of the RRDB generators on the tensor-core kernels (inference half)."""
 
     def __init__(self, gen: nn.Module, kind: str) -> None:
@@ -147,16 +194,17 @@ class RRDBEngine:
         self.num_upsample = getattr(gen, "num_upsample", 0)
         self._gen_ref = [gen]  # no nn.Module registration (avoid a reference cycle in the module tree)
         self.arena = WeightArena()
+        self.plans: Dict[str, List[Tuple[str, int, int, int]]] = {}
         g = gen
         for i, rrdb in enumerate(g.rrdb):
             for r, rdb in enumerate((rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)):
                 for k in range(1, 6):
-                    self.arena.add(_fwd_blob(f"f.{i}.{r}.{k}", getattr(rdb, f"conv{k}"), self.kc))
-        self.arena.add(_fwd_blob("f.trunk", g.trunk_conv, self.kc))
+                    self._add_forward_layer(f"f.{i}.{r}.{k}", getattr(rdb, f"conv{k}"))
+        self._add_forward_layer("f.trunk", g.trunk_conv)
         if kind == "sr":
             for s in range(self.num_upsample):
-                self.arena.add(_fwd_blob(f"f.up{s}", g.upsampling[3 * s], self.kc, perm=1))
-            self.arena.add(_fwd_blob("f.hr", g.HRconv, self.kc))
+                self._add_forward_layer(f"f.up{s}", g.upsampling[3 * s], perm=1)
+            self._add_forward_layer("f.hr", g.HRconv)
         self._bufs: Dict[tuple, Dict[str, torch.Tensor]] = {}
         # how a dense block's five dependent convs are launched (ops.CHAIN_*): layer by layer is the measured
         # optimum today; XMM_CHAIN_MODE=1 selects the pipelined single-launch kernel (F=32 only)
@@ -189,11 +237,15 @@ class RRDBEngine:
     def _rdb_forward(self, name: str, buf: torch.Tensor, out: torch.Tensor, *, s0: float, s1: float,
                      r2: Optional[torch.Tensor], s2: float) -> None:
         """One ResidualDenseBlock_5C (rrdb_blocks.py:37-54): x in buf[..., :F]; result -> out[..., :F]."""
-        f, kc, a = self.nf, self.kc, self.arena
-        layers = [((buf, 0, k * f, a.ptr(f"{name}.{k}"), kc, f, buf, k * f), dict(lrelu=0.2)) for k in range(1, 5)]
-        layers.append(((buf, 0, 5 * f, a.ptr(f"{name}.5"), kc, f, out, 0),
-                       dict(s0=s0, r1=buf, r1_coff=0, s1=s1, r2=r2, r2_coff=0, s2=s2)))
-        ops.conv3x3_chain(layers, self.chain_mode)
+        f = self.nf
+        layers = []
+        for k in range(1, 5):
+            layers += self._conv(f"{name}.{k}", buf, 0, k * f, buf, k * f, lrelu=0.2)
+        layers += self._conv(f"{name}.5", buf, 0, 5 * f, out, 0, s0=s0, r1=buf, r1_coff=0, s1=s1, r2=r2, r2_coff=0, s2=s2)
+        if len(layers) == 5:
+            ops.conv3x3_chain(layers, self.chain_mode)
+        else:  # split layers (F=64): plain launches
+            self._run(layers)
 
     def _trunk_forward(self, x: torch.Tensor, rdb_bufs: List[torch.Tensor], fea: torch.Tensor,
                        trunk_out: torch.Tensor) -> None:
@@ -222,7 +274,7 @@ class RRDBEngine:
                     self._rdb_forward(f"f.{i}.{r}", cur, nxt, s0=0.04, s1=0.2, r2=x_rrdb, s2=1.0)
                 idx += 1
         last = rdb_bufs[idx % ring]
-        ops.conv3x3(last, 0, f, self.arena.ptr("f.trunk"), self.kc, f, trunk_out, 0, s0=1.0, r1=fea, r1_coff=0, s1=1.0)
+        self._run(self._conv("f.trunk", last, 0, f, trunk_out, 0, s0=1.0, r1=fea, r1_coff=0, s1=1.0))
 
     # ------------------------------------------------------------------ public
     def _check_input(self, x: torch.Tensor) -> None:
@@ -254,10 +306,9 @@ class RRDBEngine:
             return out
         cur = bufs["trunk"]
         for s in range(self.num_upsample):
-            ops.conv3x3(cur, 0, self.nf, self.arena.ptr(f"f.up{s}"), self.kc, 4 * self.nf, bufs[f"up{s}"], 0,
-                        lrelu=0.01, pixel_shuffle=1)
+            self._run(self._conv(f"f.up{s}", cur, 0, self.nf, bufs[f"up{s}"], 0, lrelu=0.01, pixel_shuffle=1))
             cur = bufs[f"up{s}"]
-        ops.conv3x3(cur, 0, self.nf, self.arena.ptr("f.hr"), self.kc, self.nf, bufs["hr"], 0, lrelu=0.2)
+        self._run(self._conv("f.hr", cur, 0, self.nf, bufs["hr"], 0, lrelu=0.2))
         hh, ww = cur.shape[1], cur.shape[2]
         out = torch.empty(b, g.out_channels, hh, ww, dtype=torch.float32, device=x.device)
         ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, clamp=True)
@@ -265,7 +316,7 @@ class RRDBEngine:
 
 
 # ---------------------------------------------------------------------- standalone blocks
-class _BlockRunner:
+class _BlockRunner(_LayerPlans):
     """RRDB / ResidualDenseBlock_5C called on their own (reference exports them from
     models/modules/__init__.py:1).  Inference only."""
 
@@ -275,9 +326,10 @@ class _BlockRunner:
             raise NotImplementedError(f"standalone dense block with nf={nf}, gc={gc}: only nf == gc in (32, 64) is built")
         self.nf, self.kc = nf, (32 if nf == 32 else 64)
         self.arena = WeightArena()
+        self.plans = {}
         for r, rdb in enumerate(rdbs):
             for k in range(1, 6):
-                self.arena.add(_fwd_blob(f"{r}.{k}", getattr(rdb, f"conv{k}"), self.kc))
+                self._add_forward_layer(f"{r}.{k}", getattr(rdb, f"conv{k}"))
         self.n = len(rdbs)
 
     def run(self, x: torch.Tensor, rrdb: bool) -> torch.Tensor:
@@ -294,10 +346,10 @@ class _BlockRunner:
             last = rrdb and r == self.n - 1
             cur, nxt = bufs[r], bufs[r + 1]
             for k in range(1, 5):
-                ops.conv3x3(cur, 0, k * f, self.arena.ptr(f"{r}.{k}"), kc, f, cur, k * f, lrelu=0.2)
-            ops.conv3x3(cur, 0, 5 * f, self.arena.ptr(f"{r}.5"), kc, f, nxt, 0, s0=0.04 if last else 0.2, r1=cur,
-                        r1_coff=0, s1=0.2 if last else 1.0, r2=bufs[0] if last else None, r2_coff=0,
-                        s2=1.0 if last else 0.0)
+                self._run(self._conv(f"{r}.{k}", cur, 0, k * f, cur, k * f, lrelu=0.2))
+            self._run(self._conv(f"{r}.5", cur, 0, 5 * f, nxt, 0, s0=0.04 if last else 0.2, r1=cur, r1_coff=0,
+                                 s1=0.2 if last else 1.0, r2=bufs[0] if last else None, r2_coff=0,
+                                 s2=1.0 if last else 0.0))
         return bufs[self.n][..., :f].permute(0, 3, 1, 2).float().contiguous()
 
 

@@ -106,10 +106,9 @@ class TrainEngine(RRDBEngine):
             return out, bufs
         cur = bufs["trunk"]
         for s in range(self.num_upsample):
-            ops.conv3x3(cur, 0, self.nf, self.arena.ptr(f"f.up{s}"), self.kc, 4 * self.nf, bufs[f"up{s}"], 0,
-                        lrelu=0.01, pixel_shuffle=1)
+            self._run(self._conv(f"f.up{s}", cur, 0, self.nf, bufs[f"up{s}"], 0, lrelu=0.01, pixel_shuffle=1))
             cur = bufs[f"up{s}"]
-        ops.conv3x3(cur, 0, self.nf, self.arena.ptr("f.hr"), self.kc, self.nf, bufs["hr"], 0, lrelu=0.2)
+        self._run(self._conv("f.hr", cur, 0, self.nf, bufs["hr"], 0, lrelu=0.2))
         out = torch.empty(b, g.out_channels, cur.shape[1], cur.shape[2], dtype=torch.float32, device=x.device)
         ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, pre=bufs["pre"])
         return out, bufs
