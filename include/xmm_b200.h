@@ -146,6 +146,29 @@ int xmm_normalize(const xmm_normalize_params* p, void* stream);
 int xmm_denormalize(const float* in, float* out, size_t n, size_t per_image, const float* max_vals_dev,
                     int max_n, int stretch_mode, void* stream);
 
+/* out = norm_to(denorm_from(in)), element-wise: the re-normalisation XMMMetricCollection.update applies
+ * before every metric (metrics/xmm_metric_collection.py:135-143), as one pass.                           */
+int xmm_restretch(const float* in, float* out, size_t n, int from_mode, int to_mode, void* stream);
+
+/* The per-batch data feed (data/dataset.py:24-49,258-270; data/tools.py:103-126) on raw count planes that are
+ * already in device memory: sum of up to 3 planes (image, AGN, background) x detector mask, optional
+ * ImageUpsample, zero-pad / crop to res_h x res_w (floor(diff/2) before), counts -> rate, Normalize.       */
+typedef struct {
+  const void* src[3];  /* [batch][h][w] int32 or fp32; src[0] required                                    */
+  int nsrc;
+  int src_is_int32;
+  const unsigned char* mask; /* [h][w] or NULL                                                              */
+  int batch, h, w;
+  int up;              /* integer ImageUpsample factor (1 = none)                                          */
+  int res_h, res_w;    /* output image size                                                                */
+  float pre_scale;     /* 1/exposure                                                                       */
+  const float* pre_scale_dev; /* optional per-image factor [batch] (multiplied with pre_scale)            */
+  float max_val;       /* > 0                                                                              */
+  int stretch_mode;
+  float* out;          /* [batch][res_h][res_w] fp32                                                       */
+} xmm_prepare_counts_params;
+int xmm_prepare_counts(const xmm_prepare_counts_params* p, void* stream);
+
 /* Replaces ImageUpsample.__call__ (transforms/imageupsample.py:10-26): nearest upsample by an
  * integer factor then divide by factor^2.  in [n_img][h][w] fp32 -> out [n_img][h*s][w*s].  */
 int xmm_image_upsample(const float* in, float* out, int n_img, int h, int w, int scale, void* stream);

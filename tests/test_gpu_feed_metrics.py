@@ -1,0 +1,150 @@
+"""GPU (B200): the widened rows of SURVEY.md section 8(f) -- validation metric collection (f2) and the fused data
+feed (f3) -- against the oracle restatement of the reference arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rrdb_oracle as O
+from oracle.synthetic import count_batch, detector_mask
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+LR_MAX, HR_MAX = 0.0022336, 0.0005584
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from xmm_superres_denoise_b200 import _lib
+
+    _lib.check(_lib.load().xmm_check_device())
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------ f3: data feed
+@pytest.mark.parametrize("mode", ["linear", "sqrt", "asinh", "log"])
+@pytest.mark.parametrize("planes,upsample", [(1, 1), (3, 1), (1, 2)])
+def test_prepare_counts_matches_reference_pipeline(dev, mode, planes, upsample):
+    """int32 planes -> (sum) * mask -> [upsample] -> pad 411x403 -> 416 (832) -> /exposure -> Normalize, one kernel,
+    vs dataset.py:24-49 + tools.py:103-126 + normalize.py:66-82 restated by the oracle."""
+    from xmm_superres_denoise_b200.data import load_and_combine_simulations
+    from xmm_superres_denoise_b200.transforms import Normalize
+
+    rng = np.random.default_rng(11 + planes + upsample)
+    b, h, w = 3, 411, 403
+    srcs = [rng.poisson(lam, size=(b, h, w)).astype(np.int32) for lam in (1.0, 0.05, 0.1)[:planes]]
+    mask = detector_mask(1)
+    exposure = 20000.0
+    res = 416 * upsample
+    tens = [torch.from_numpy(s) for s in srcs]
+    if upsample == 1:
+        combined = O.combine_mask_pad(tens[0][:, None], tens[1][:, None] if planes > 1 else None,
+                                      tens[2][:, None] if planes > 2 else None,
+                                      torch.from_numpy(mask.astype(np.float32)), res)
+    else:  # ImageUpsample sits between the mask multiply and the padding (dataset.py:41-47)
+        comb = sum(t.float() for t in tens)[:, None] * torch.from_numpy(mask.astype(np.float32))
+        up = O.image_upsample(comb, upsample)
+        top, left = (res - h * upsample) // 2, (res - w * upsample) // 2
+        combined = torch.nn.functional.pad(up, (left, res - w * upsample - left, top, res - h * upsample - top))
+    want = O.normalize_image(combined / exposure, LR_MAX, mode)
+    norm = Normalize(LR_MAX, HR_MAX, mode)
+    got = load_and_combine_simulations(res, tens[0].to(dev), tens[1].to(dev) if planes > 1 else None,
+                                       tens[2].to(dev) if planes > 2 else None, torch.from_numpy(mask).to(dev),
+                                       upsample, normalizer=norm, which="lr", exposure=exposure).cpu()
+    assert got.shape == (b, 1, res, res)
+    assert torch.allclose(got, want, atol=2e-6, rtol=1e-5), float((got - want).abs().max())
+    assert float(got[:, :, :2].abs().max()) == 0.0  # the padded border is exactly zero
+
+
+def test_prepare_counts_per_image_exposure_and_crop(dev):
+    from xmm_superres_denoise_b200 import ops
+
+    rng = np.random.default_rng(5)
+    src = torch.from_numpy(rng.poisson(2.0, size=(2, 40, 52)).astype(np.float32))
+    expo = torch.tensor([10.0, 40.0])
+    got = ops.prepare_counts([src.to(dev)], (32, 44), 0.5, "sqrt", exposure=expo.to(dev)).cpu()
+    top, left = (32 - 40) // 2, (44 - 52) // 2  # negative: crop, floor(diff/2) first (tools.py:111-117)
+    crop = torch.nn.functional.pad(src[:, None], (left, 44 - 52 - left, top, 32 - 40 - top))
+    want = O.normalize_image(crop / expo.view(2, 1, 1, 1), 0.5, "sqrt")
+    assert torch.allclose(got, want, atol=2e-6, rtol=1e-5)
+
+
+def test_counts_feed_double_buffering(dev):
+    from xmm_superres_denoise_b200.data import CountsFeed
+    from xmm_superres_denoise_b200.transforms import Normalize
+
+    norm = Normalize(LR_MAX, HR_MAX, "sqrt")
+    mask = detector_mask(1)
+    feed = CountsFeed(2, 411, 403, 416, norm, det_mask=mask)
+    rng = np.random.default_rng(0)
+    batches = [rng.poisson(1.0, size=(2, 411, 403)).astype(np.int32) for _ in range(5)]
+    outs = []
+    feed.submit([batches[0]], exposure=20000.0)
+    for i in range(5):
+        if i + 1 < 5:
+            feed.submit([batches[i + 1]], exposure=20000.0)
+        outs.append(feed.get().clone())
+    torch.cuda.synchronize()
+    for bt, got in zip(batches, outs):
+        comb = O.combine_mask_pad(torch.from_numpy(bt)[:, None], None, None, torch.from_numpy(mask.astype(np.float32)), 416)
+        want = O.normalize_image(comb / 20000.0, LR_MAX, "sqrt")
+        assert torch.allclose(got.cpu(), want, atol=2e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------ f2: validation metrics
+def test_metric_collection_matches_oracle(dev):
+    """Two updates of get_metrics (dataset normaliser sqrt; scaling normalisers linear + sqrt) vs the oracle's
+    restatement of torchmetrics' accumulation (xmm_metric_collection.py:14-38,135-143)."""
+    from xmm_superres_denoise_b200.metrics import get_in_metrics, get_metrics
+    from xmm_superres_denoise_b200.transforms import Normalize
+
+    ds = Normalize(LR_MAX, LR_MAX, "sqrt")
+    scal = [Normalize(LR_MAX, LR_MAX, "linear"), Normalize(LR_MAX, LR_MAX, "sqrt")]
+    coll = get_metrics(ds, scal, "val")
+    assert sorted(coll.keys()) == sorted(f"val/{m}/{n}" for m in ("linear", "sqrt")
+                                         for n in ("psnr", "ssim", "ms_ssim", "l1", "l2", "poisson"))
+    batches = []
+    for seed in (1, 2):
+        lr, hr, t_lr, t_hr = count_batch(2, seed=seed, kind="dn")
+        t = O.normalize_image(torch.from_numpy(hr.astype(np.float32) / t_hr), LR_MAX, "sqrt")
+        g = torch.Generator().manual_seed(seed)
+        p = (t * (0.9 + 0.2 * torch.rand(t.shape, generator=g)) + 0.01 * torch.rand(t.shape, generator=g)).clamp(0, 1)
+        batches.append((p, t))
+        coll.update(preds=p.to(dev), target=t.to(dev))
+    got = {k: float(v) for k, v in coll.compute().items()}
+    for mode in ("linear", "sqrt"):
+        ps = [O.stretch(O.unstretch(p, "sqrt"), mode) for p, _ in batches]
+        ts = [O.stretch(O.unstretch(t, "sqrt"), mode) for _, t in batches]
+        n = sum(p.numel() for p in ps)
+        nb = sum(p.shape[0] for p in ps)
+        absum = sum(float((p - t).abs().double().sum()) for p, t in zip(ps, ts))
+        sq = sum(float(((p - t).double() ** 2).sum()) for p, t in zip(ps, ts))
+        tmin = min(0.0, min(float(t.min()) for t in ts))
+        tmax = max(0.0, max(float(t.max()) for t in ts))
+        want = {
+            "l1": absum / n, "l2": sq / n,
+            "psnr": 10.0 * np.log10((tmax - tmin) ** 2 / (sq / n)),
+            "poisson": sum(float(torch.nn.functional.poisson_nll_loss(p, t, log_input=False)) for p, t in zip(ps, ts)) / nb,
+            "ssim": sum(float(O.ssim(p, t)) * p.shape[0] for p, t in zip(ps, ts)) / nb,
+            "ms_ssim": sum(float(O.ms_ssim(p, t)) * p.shape[0] for p, t in zip(ps, ts)) / nb,
+        }
+        for name, w in want.items():
+            g = got[f"val/{mode}/{name}"]
+            assert abs(g - w) <= 2e-4 * max(1.0, abs(w)), (mode, name, g, w)
+    coll.reset()
+    with pytest.raises(RuntimeError):
+        coll.compute()
+    inm = get_in_metrics(ds, scal, "val")
+    assert "val/linear/in/psnr" in inm.keys()
+
+
+def test_restretch_roundtrip(dev):
+    from xmm_superres_denoise_b200 import ops
+
+    x = torch.rand(3, 1, 37, 41, generator=torch.Generator().manual_seed(2))
+    for a in ("linear", "sqrt", "asinh", "log"):
+        for b in ("linear", "sqrt", "asinh", "log"):
+            got = ops.restretch(x.to(dev), a, b).cpu()
+            want = O.stretch(O.unstretch(x, a), b)
+            assert torch.allclose(got, want, atol=3e-6, rtol=2e-5), (a, b, float((got - want).abs().max()))

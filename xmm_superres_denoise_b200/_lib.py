@@ -109,11 +109,18 @@ class MsssimFinalizeParams(Structure):
                 ("gl_dev", c_void_p), ("weight", c_float)]
 
 
+class PrepareCountsParams(Structure):
+    _fields_ = [("src", c_void_p * 3), ("nsrc", c_int), ("src_is_int32", c_int), ("mask", c_void_p),
+                ("batch", c_int), ("h", c_int), ("w", c_int), ("up", c_int), ("res_h", c_int), ("res_w", c_int),
+                ("pre_scale", c_float), ("pre_scale_dev", c_void_p), ("max_val", c_float), ("stretch_mode", c_int),
+                ("out", c_void_p)]
+
+
 class ColsumSegment(Structure):
     _fields_ = [("c0", c_int), ("n", c_int), ("out", c_void_p), ("scale", c_float), ("accumulate", c_int)]
 
 
-EXTRA_STRUCTS = {"xmm_colsum_segment": ColsumSegment, "xmm_scale_stats": ScaleStats, "xmm_ssim_stats_params": SsimStatsParams,
+EXTRA_STRUCTS = {"xmm_colsum_segment": ColsumSegment, "xmm_prepare_counts_params": PrepareCountsParams, "xmm_scale_stats": ScaleStats, "xmm_ssim_stats_params": SsimStatsParams,
                  "xmm_ssim_grad_params": SsimGradParams, "xmm_msssim_finalize_params": MsssimFinalizeParams,
                  "xmm_wgrad_role": WgradRole, "xmm_wgrad_dst": WgradDst, "xmm_wgrad_params": WgradParams,
                  "xmm_edge_wgrad_params": EdgeWgradParams}
@@ -131,6 +138,8 @@ SIGNATURES = {
     "xmm_conv3x3_chain_bf16": (c_int, [POINTER(Conv3x3Params), c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "xmm_normalize": (c_int, [POINTER(NormalizeParams), c_void_p]),
     "xmm_denormalize": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_int, c_void_p]),
+    "xmm_restretch": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "xmm_prepare_counts": (c_int, [POINTER(PrepareCountsParams), c_void_p]),
     "xmm_image_upsample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xmm_conv_first": (c_int, [POINTER(ConvFirstParams), c_void_p]),
     "xmm_conv_last": (c_int, [POINTER(ConvLastParams), c_void_p]),

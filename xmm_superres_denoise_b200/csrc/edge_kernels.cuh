@@ -94,6 +94,74 @@ __global__ void denormalize_kernel(const float* __restrict__ in, float* __restri
   out[i] = fminf(fmaxf(v, 0.0f), mx);
 }
 
+// out = norm_to(denorm_from(x)): the validation metric collection evaluates every metric under several
+// normalisers (metrics/xmm_metric_collection.py:135-143: dataset_normalizer.denorm, then normalizer.norm) --
+// one pass, 8 B per pixel, instead of two.
+__global__ void restretch_kernel(const float* __restrict__ in, float* __restrict__ out, size_t n, int mode_from,
+                                 int mode_to) {
+  const size_t i4 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (n - i4 >= 4) {
+    float4 q = *reinterpret_cast<const float4*>(in + i4);
+    q.x = stretch_fwd(stretch_inv(q.x, mode_from), mode_to);
+    q.y = stretch_fwd(stretch_inv(q.y, mode_from), mode_to);
+    q.z = stretch_fwd(stretch_inv(q.z, mode_from), mode_to);
+    q.w = stretch_fwd(stretch_inv(q.w, mode_from), mode_to);
+    *reinterpret_cast<float4*>(out + i4) = q;
+  } else {
+    for (size_t i = i4; i < n; ++i) out[i] = stretch_fwd(stretch_inv(in[i], mode_from), mode_to);
+  }
+}
+
+// The data feed of one batch (data/dataset.py:24-49 _load_and_combine_simulations, data/tools.py:103-126
+// reshape_img_to_res, data/dataset.py:258-270 normalisation), from raw FITS planes already in device memory:
+//   v = (img + agn + bkg) * det_mask            int32 or fp32 counts, [B][h][w]; mask [h][w], broadcast
+//   v = nearest-upsample(v, up) / up^2           optional ImageUpsample (real-SR targets)
+//   zero-pad (or crop) to res_h x res_w with floor(diff/2) before, the rest after
+//   out = clamp(stretch(clamp(v * pre_scale, 0, max) / max), 0, 1)       pre_scale = 1/exposure
+// One thread per output pixel: 4..12 B read (+1 mask) and 4 B written.
+struct PrepareCountsArgs {
+  const void* src[3];
+  int nsrc, src_is_int32;
+  const uint8_t* mask;
+  int batch, h, w, up, res_h, res_w;
+  float pre_scale;
+  const float* pre_scale_dev;  // optional per-image scale (B floats), multiplied with pre_scale
+  float max_val;
+  int mode;
+  float* out;
+};
+
+__global__ void prepare_counts_kernel(const PrepareCountsArgs a) {
+  const size_t n = size_t(a.batch) * a.res_h * a.res_w;
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int X = int(i % a.res_w);
+  const size_t t = i / a.res_w;
+  const int Y = int(t % a.res_h);
+  const int b = int(t / a.res_h);
+  const int uh = a.h * a.up, uw = a.w * a.up;
+  // floor division (a negative difference crops, as torch.nn.functional.pad with negative pads does)
+  const int dyv = a.res_h - uh, dxv = a.res_w - uw;
+  const int top = (dyv >= 0) ? dyv / 2 : -((-dyv + 1) / 2);
+  const int left = (dxv >= 0) ? dxv / 2 : -((-dxv + 1) / 2);
+  const int y = Y - top, x = X - left;
+  float v = 0.0f;
+  if (y >= 0 && y < uh && x >= 0 && x < uw) {
+    const size_t sidx = (size_t(b) * a.h + y / a.up) * a.w + x / a.up;
+    for (int k = 0; k < a.nsrc; ++k)
+      v += a.src_is_int32 ? float(static_cast<const int*>(a.src[k])[sidx]) : static_cast<const float*>(a.src[k])[sidx];
+    if (a.mask != nullptr) v *= float(a.mask[size_t(y / a.up) * a.w + x / a.up]);
+    if (a.up > 1) v /= float(a.up * a.up);
+  }
+  float sc = a.pre_scale;
+  if (a.pre_scale_dev != nullptr) sc *= a.pre_scale_dev[b];
+  v *= sc;
+  v = fminf(fmaxf(v, 0.0f), a.max_val);
+  v = stretch_fwd(v / a.max_val, a.mode);
+  a.out[i] = fminf(fmaxf(v, 0.0f), 1.0f);
+}
+
 // max over a float array (normalize's max_val <= 0 branch): atomicMax on the int view is valid for
 // non-negative floats; negative inputs clamp to 0 which matches a counts image.
 __global__ void max_kernel(const float* __restrict__ in, size_t n, float pre_scale, float* __restrict__ out) {

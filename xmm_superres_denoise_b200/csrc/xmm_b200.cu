@@ -497,6 +497,48 @@ extern "C" int xmm_denormalize(const float* in, float* out, size_t n, size_t per
   return XMM_OK;
 }
 
+extern "C" int xmm_restretch(const float* in, float* out, size_t n, int from_mode, int to_mode, void* stream) {
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  if (n == 0) return XMM_OK;
+  XMM_REQUIRE(in && out, "restretch: null tensor pointer");
+  XMM_REQUIRE(from_mode >= 0 && from_mode <= 3 && to_mode >= 0 && to_mode <= 3,
+              "restretch: Stretching function %d -> %d is not implemented", from_mode, to_mode);
+  XMM_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "restretch: pointers must be 16-byte aligned");
+  const size_t threads = (n + 3) / 4;
+  restretch_kernel<<<unsigned((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, n, from_mode,
+                                                                                                  to_mode);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+extern "C" int xmm_prepare_counts(const xmm_prepare_counts_params* pp, void* stream) {
+  XMM_REQUIRE(pp != nullptr, "prepare_counts: null params");
+  const xmm_prepare_counts_params& p = *pp;
+  DeviceInfo dev;
+  int rc = require_sm100(&dev);
+  if (rc != XMM_OK) return rc;
+  XMM_REQUIRE(p.nsrc >= 1 && p.nsrc <= 3 && p.src[0] && p.out, "prepare_counts: 1..3 source planes and an output");
+  for (int k = 0; k < p.nsrc; ++k) XMM_REQUIRE(p.src[k] != nullptr, "prepare_counts: source plane %d is null", k);
+  XMM_REQUIRE(p.batch > 0 && p.h > 0 && p.w > 0 && p.res_h > 0 && p.res_w > 0 && p.up >= 1,
+              "prepare_counts: bad shape %dx%dx%d (x%d) -> %dx%d", p.batch, p.h, p.w, p.up, p.res_h, p.res_w);
+  XMM_REQUIRE(p.max_val > 0.0f, "prepare_counts: max_val must be positive");
+  XMM_REQUIRE(p.stretch_mode >= 0 && p.stretch_mode <= 3, "prepare_counts: Stretching function %d is not implemented",
+              p.stretch_mode);
+  PrepareCountsArgs a{};
+  for (int k = 0; k < 3; ++k) a.src[k] = k < p.nsrc ? p.src[k] : nullptr;
+  a.nsrc = p.nsrc; a.src_is_int32 = p.src_is_int32; a.mask = p.mask;
+  a.batch = p.batch; a.h = p.h; a.w = p.w; a.up = p.up; a.res_h = p.res_h; a.res_w = p.res_w;
+  a.pre_scale = p.pre_scale; a.pre_scale_dev = p.pre_scale_dev; a.max_val = p.max_val; a.mode = p.stretch_mode;
+  a.out = p.out;
+  const size_t n = size_t(p.batch) * p.res_h * p.res_w;
+  prepare_counts_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
 extern "C" int xmm_image_upsample(const float* in, float* out, int n_img, int h, int w, int scale, void* stream) {
   DeviceInfo dev;
   int rc = require_sm100(&dev);

@@ -198,6 +198,70 @@ def denormalize(inp: torch.Tensor, max_vals: torch.Tensor, stretch_mode: str) ->
     return out
 
 
+def restretch(x: torch.Tensor, from_mode: str, to_mode: str) -> torch.Tensor:
+    """norm_to(denorm_from(x)) in one pass (metrics/xmm_metric_collection.py:135-143)."""
+    for m in (from_mode, to_mode):
+        if m not in _lib.STRETCH_MODES:
+            raise ValueError(f"Stretching function {m} is not implemented")
+    _lib.require_cuda_tensor(x, torch.float32, "restretch input")
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().xmm_restretch(x.data_ptr(), out.data_ptr(), x.numel(), _lib.STRETCH_MODES[from_mode],
+                                         _lib.STRETCH_MODES[to_mode], _lib.stream_ptr()))
+    _count()
+    return out
+
+
+def prepare_counts(planes, res, max_val: float, stretch_mode: str, *, det_mask: Optional[torch.Tensor] = None,
+                   exposure=1.0, upsample: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw count planes -> normalised network input, one kernel (data/dataset.py:24-49,258-270).
+
+    planes: 1..3 tensors [B,h,w] or [B,1,h,w] (image, AGN, background), all int32 or all fp32, on the GPU;
+    res: int or (res_h, res_w); exposure: seconds, a float or a [B] tensor; returns [B,1,res_h,res_w] fp32."""
+    if stretch_mode not in _lib.STRETCH_MODES:
+        raise ValueError(f"Stretching function {stretch_mode} is not implemented")
+    planes = [p for p in planes if p is not None]
+    if not 1 <= len(planes) <= 3:
+        raise RuntimeError("prepare_counts: 1..3 source planes")
+    first = planes[0]
+    if first.dim() == 4:
+        if first.shape[1] != 1:
+            raise RuntimeError("prepare_counts: single-channel count images only")
+        planes = [p.reshape(p.shape[0], p.shape[2], p.shape[3]) for p in planes]
+        first = planes[0]
+    b, h, w = first.shape
+    for p in planes:
+        if not p.is_cuda or not p.is_contiguous() or p.dtype != first.dtype or p.shape != first.shape:
+            raise RuntimeError("prepare_counts: planes must be contiguous CUDA tensors of one dtype and shape")
+    if first.dtype not in (torch.int32, torch.float32):
+        raise RuntimeError("prepare_counts: planes must be int32 or fp32")
+    res_h, res_w = (res, res) if isinstance(res, int) else res
+    if out is None:
+        out = torch.empty(b, 1, res_h, res_w, dtype=torch.float32, device=first.device)
+    _lib.require_cuda_tensor(out, torch.float32, "prepare_counts output")
+    p = _lib.PrepareCountsParams()
+    for k, t in enumerate(planes):
+        p.src[k] = t.data_ptr()
+    p.nsrc, p.src_is_int32 = len(planes), int(first.dtype == torch.int32)
+    if det_mask is not None:
+        _lib.require_cuda_tensor(det_mask, torch.uint8, "prepare_counts det_mask")
+        if det_mask.numel() != h * w:
+            raise RuntimeError("prepare_counts: det_mask must have the shape of one source image")
+        p.mask = det_mask.data_ptr()
+    p.batch, p.h, p.w, p.up, p.res_h, p.res_w = b, h, w, int(upsample), res_h, res_w
+    keep = None
+    if isinstance(exposure, torch.Tensor):
+        keep = (1.0 / exposure.to(device=first.device, dtype=torch.float32)).reshape(-1).contiguous()
+        if keep.numel() != b:
+            raise RuntimeError("prepare_counts: one exposure per image")
+        p.pre_scale, p.pre_scale_dev = 1.0, keep.data_ptr()
+    else:
+        p.pre_scale = 1.0 / float(exposure)
+    p.max_val, p.stretch_mode, p.out = float(max_val), _lib.STRETCH_MODES[stretch_mode], out.data_ptr()
+    _lib.check(_lib.load().xmm_prepare_counts(ctypes.byref(p), _lib.stream_ptr()))
+    _count()
+    return out
+
+
 def image_upsample(x: torch.Tensor, scale: int) -> torch.Tensor:
     """Nearest upsample by an integer factor, divided by factor**2 (imageupsample.py:10-26)."""
     _lib.require_cuda_tensor(x, torch.float32, "image_upsample input")
