@@ -148,3 +148,50 @@ def test_restretch_roundtrip(dev):
             got = ops.restretch(x.to(dev), a, b).cpu()
             want = O.stretch(O.unstretch(x, a), b)
             assert torch.allclose(got, want, atol=3e-6, rtol=2e-5), (a, b, float((got - want).abs().max()))
+
+
+# ------------------------------------------------------------------------------ f4: inference on FITS files
+@pytest.mark.parametrize("kind", ["dn", "sr"])
+def test_run_inference_on_fits_files(dev, tmp_path, golden_dir, kind):
+    """FITS in -> FITS out through utils.run_inference_on_file (reference lines 101-200): the written prediction
+    equals denormalize_hr(generator(normalize_lr(pad(counts * mask) / exposure))) computed by the oracle, the input
+    copy is the padded rate image, and the WCS keywords follow filehandling.py:197-225."""
+    import os
+
+    from xmm_superres_denoise_b200.utils import fits_io
+    from xmm_superres_denoise_b200.utils.run_inference_on_file import build_generator, infer_files
+
+    g = np.load(os.path.join(golden_dir, "config1_dn_example.npz"))
+    counts = g["counts"].astype(np.int32)  # one real 20 ks example image (411 x 403)
+    mask = detector_mask(1)
+    files = []
+    for i in range(3):
+        p = str(tmp_path / f"obs{i}_image.fits")
+        fits_io.write_primary(p, np.roll(counts, 7 * i, axis=1), {"EXPOSURE": 20000.0, "CRPIX1": 1.0, "CRPIX2": 1.0,
+                                                                   "CDELT1": 80.0, "CDELT2": 80.0, "PA_PNT": 100.0})
+        files.append(p)
+    cfg = {"lr_res": 416, "hr_res": 832 if kind == "sr" else 416, "dataset_lr_res": 416, "data_scaling": "sqrt",
+           "lr_max": LR_MAX, "hr_max": HR_MAX if kind == "sr" else LR_MAX, "hr_exp": 100 if kind == "sr" else 50,
+           "det_mask": True}
+    with pytest.warns(UserWarning, match="randomly initialised"):
+        gen = build_generator(cfg, {"filters": 32, "residual_blocks": 1}, None, dev)
+    sd = {k: v.detach().cpu() for k, v in gen.state_dict().items()}
+    res = infer_files(files, cfg, str(tmp_path / "out"), gen, det_mask=mask, batch_size=2)
+    assert len(res) == 3
+    for i, r in enumerate(res):
+        img_in, h_in = fits_io.read_primary(r["input"])
+        img_out, h_out = fits_io.read_primary(r["predict"])
+        comb = O.combine_mask_pad(torch.from_numpy(np.roll(counts, 7 * i, axis=1))[None, None], None, None,
+                                  torch.from_numpy(mask.astype(np.float32)), 416)
+        x = O.normalize_image(comb / 20000.0, LR_MAX, "sqrt")
+        want_in = O.denormalize_image(x, torch.tensor(LR_MAX), "sqrt")[0, 0].numpy()
+        assert img_in.shape == (416, 416) and np.allclose(img_in, want_in, atol=1e-9, rtol=1e-5)
+        with torch.no_grad():
+            y = O.model_forward(x, sd, kind, 1)
+        want_out = O.denormalize_image(y, torch.tensor(cfg["hr_max"]), "sqrt")[0, 0].numpy()
+        assert img_out.shape == want_out.shape
+        assert rel_l2(img_out, want_out) < 2e-2  # bf16 generator, de-normalised (squared) output
+        assert h_in["CRPIX1"] == 7.0 and h_in["CRPIX2"] == 3.0 and h_in["EXPOSURE"] == 20000.0
+        if kind == "sr":
+            assert h_out["CRPIX1"] == 14.5 and h_out["CDELT1"] == 40.0 and "CD1_1" in h_out
+            assert h_out["EXPOSURE"] == 100000.0
