@@ -195,3 +195,41 @@ def test_run_inference_on_fits_files(dev, tmp_path, golden_dir, kind):
         if kind == "sr":
             assert h_out["CRPIX1"] == 14.5 and h_out["CDELT1"] == 40.0 and "CD1_1" in h_out
             assert h_out["EXPOSURE"] == 100000.0
+
+
+def test_model_wrapper_train_and_validation_steps(dev):
+    """models.Model (the reference's LightningModule surface) on the CUDA path: a training step returns the
+    differentiable loss, a validation epoch accumulates loss + metric collections and logs them by name."""
+    import types
+
+    from xmm_superres_denoise_b200.metrics import get_in_metrics, get_metrics
+    from xmm_superres_denoise_b200.models import Model
+    from xmm_superres_denoise_b200.transforms import Normalize
+    from xmm_superres_denoise_b200.utils.loss_functions import create_loss
+
+    cfg = types.SimpleNamespace(name="rrdb_denoise", memory_efficient=False, batch_size=2,
+                                model=types.SimpleNamespace(in_channels=1, out_channels=1, filters=32, residual_blocks=1),
+                                optimizer=types.SimpleNamespace(learning_rate=1e-4, betas=(0.9, 0.999)))
+    ds = Normalize(LR_MAX, LR_MAX, "sqrt")
+    scal = [Normalize(LR_MAX, LR_MAX, "linear")]
+    loss = create_loss(None, {"l1": 0.5, "poisson": 0.5})
+    m = Model(cfg, (416, 416), (416, 416), loss, get_metrics(ds, scal, "val"), None, get_in_metrics(ds, scal, "val"), None)
+    m.configure_model()
+    m = m.to(dev)
+    lr, hr, t_lr, t_hr = count_batch(2, seed=4, kind="dn")
+    x = O.normalize_image(torch.from_numpy(lr.astype(np.float32) / t_lr), LR_MAX, "sqrt").to(dev)
+    y = O.normalize_image(torch.from_numpy(hr.astype(np.float32) / t_hr), LR_MAX, "sqrt").to(dev)
+    opt = m.configure_optimizers()
+    m.train()
+    l0 = m.training_step((x, y), 0)
+    l0.backward()
+    opt.step()
+    assert torch.isfinite(l0) and all(p.grad is not None for p in m.model.parameters())
+    m.eval()
+    m.on_validation_start()
+    with torch.no_grad():
+        m.validation_step((x, y), 0)
+    m.on_validation_epoch_end()
+    for k in ("val/loss", "val/linear/psnr", "val/linear/ms_ssim", "val/linear/in/l1"):
+        assert k in m.logged and torch.isfinite(torch.as_tensor(m.logged[k])), k
+    assert m.in_metrics is None  # logged once (model.py:136-139)

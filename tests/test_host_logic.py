@@ -64,3 +64,33 @@ def test_normalize_interface():
         Normalize(1.0, 1.0, "cbrt")
     with pytest.raises(ValueError):
         ImageUpsample(1.5)
+
+
+def test_model_wrapper_mirrors_reference_interface():
+    """models.Model: constructor / method names of the reference's LightningModule (models/model.py:13-247)."""
+    import types
+
+    from xmm_superres_denoise_b200.models import Model
+
+    cfg = types.SimpleNamespace(name="esr_gen", memory_efficient=False, batch_size=4,
+                                model=types.SimpleNamespace(in_channels=1, out_channels=1, filters=32, residual_blocks=1),
+                                optimizer=types.SimpleNamespace(learning_rate=1e-4, betas=(0.9, 0.999)))
+    m = Model(cfg, (416, 416), (832, 832), loss=None, metrics=None, extended_metrics=None, in_metrics=None,
+              in_extended_metrics=None)
+    assert m.model is None
+    m.configure_model()
+    assert type(m.model).__name__ == "GeneratorRRDB_SR" and m.model.num_upsample == 1
+    opt = m.configure_optimizers()
+    assert opt.defaults["lr"] == 1e-4 and tuple(opt.defaults["betas"]) == (0.9, 0.999)
+    for name in ("forward", "training_step", "validation_step", "test_step", "on_validation_start",
+                 "on_validation_epoch_end", "on_test_epoch_end", "_on_step", "_on_epoch_end"):
+        assert callable(getattr(m, name))
+    cfg.name = "swinfir"
+    m2 = Model(cfg, (416, 416), (416, 416), loss=None)
+    import pytest
+
+    with pytest.raises(NotImplementedError):
+        m2.configure_model()
+    bad = Model(types.SimpleNamespace(**{**cfg.__dict__, "name": "esr_gen"}), (416, 416), (1248, 1248), loss=None)
+    with pytest.raises(ValueError):
+        bad.configure_model()
