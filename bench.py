@@ -46,6 +46,19 @@ def peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
 
 
+def traffic_from_profile(batch: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/
+    r01_traffic.json: bytes per launch of conv3x3_dx_kernel<32,32> with cin=160, scaled linearly in the batch)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    per_image = t["dram_bytes_per_launch"] / t["batch"]
+    return {"bytes_per_launch": per_image * batch, "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_image"] * batch,
+            "kernel": t["kernel"], "source": t["source"]}
+
+
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU every 100 ms while the timed region runs."""
@@ -340,7 +353,7 @@ def main() -> None:
 
     # ---------------------------------------------------------------- device-resident timing
     prof_events = []
-    orig_conv = ops.conv3x3
+    orig_conv, orig_chain = ops.conv3x3, ops.conv3x3_chain
 
     def conv_profiled(inp, in_coff, cin, wptr, kc, cout, out, out_coff, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -348,7 +361,18 @@ def main() -> None:
         orig_conv(inp, in_coff, cin, wptr, kc, cout, out, out_coff, **kw)
         e1.record()
         if cout == NF and inp.shape[3] == 5 * NF:  # dense-block layers = the dominant kernel instantiation
-            prof_events.append((e0, e1, 2.0 * 9 * cin * cout * inp.shape[0] * inp.shape[1] * inp.shape[2]))
+            prof_events.append((e0, e1, 2.0 * 9 * cin * cout * inp.shape[0] * inp.shape[1] * inp.shape[2], 1))
+
+    def chain_profiled(layers, mode=0):
+        # one dense block: its five conv launches back to back (or one pipelined launch), bracketed by two events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_chain(layers, mode)
+        e1.record()
+        flop = 0.0
+        for (inp, _coff, cin, _w, _kc, cout, _out, _ocoff), _kw in layers:
+            flop += 2.0 * 9 * cin * cout * inp.shape[0] * inp.shape[1] * inp.shape[2]
+        prof_events.append((e0, e1, flop, 1 if mode == ops.CHAIN_PIPELINED else len(layers)))
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -356,6 +380,7 @@ def main() -> None:
         import xmm_superres_denoise_b200.engine as engine_mod
 
         engine_mod.ops.conv3x3 = conv_profiled
+        engine_mod.ops.conv3x3_chain = chain_profiled
         ops.LAUNCHES = 0
         barrier()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -366,11 +391,12 @@ def main() -> None:
             stop.record()
             barrier()
         engine_mod.ops.conv3x3 = orig_conv
+        engine_mod.ops.conv3x3_chain = orig_chain
         launches = ops.LAUNCHES
         ms_total = start.elapsed_time(stop)
-        k_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in prof_events)
-        k_flop = sum(f for _, _, f in prof_events)
-        n_k = len(prof_events)
+        k_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in prof_events)
+        k_flop = sum(f for _, _, f, _ in prof_events)
+        n_k = sum(n for _, _, _, n in prof_events)
 
         # ------------------------------------------------------------ end to end (host buffers)
         def e2e_step():
@@ -427,11 +453,13 @@ def main() -> None:
         "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": counts_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel<KC=32,NT=32> (dense-block 3x3 convs)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "dense-block 3x3 convs: conv3x3_dx_kernel<32,32> (cin 64..160) + conv3x3_tc_kernel<32,32> "
+                               "(cin 32), timed per block of 5 launches",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_sustained"], "frac_of_burst": achieved / pk["bf16_burst"],
                      "peak_src": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                     "launches_timed": n_k, "share_of_step": k_ms / ms_total, "traffic": None,
+                     "launches_timed": n_k, "share_of_step": k_ms / ms_total, "traffic": traffic_from_profile(B),
                      "whole_step_tflops": total_flop * args.steps / (ms_total * 1e-3) / 1e12},
     }
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only

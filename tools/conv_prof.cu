@@ -59,7 +59,7 @@ static void run(int B, int H, int W, int k, int stages_cap) {
   if (make_nhwc_tmap(&tmap, in_d, B, H, W, ctot, KC, DX ? kDxTileW : kTileW + 2, DX ? kDxPatchH : kHaloH, false) != 0) { printf("tmap failed\n"); exit(2); }
   a.prof = prof;
   CUtensorMap tmap_o = tmap;
-  if (DX && make_nhwc_tmap(&tmap_o, out_d, B, H, W, ctot, NT, kDxTileW, kDxTileH, false) != 0) { printf("tmap failed\n"); exit(2); }
+  if (DX && make_nhwc_tmap(&tmap_o, out_d, B, H, W, ctot, NT / 2, kDxTileW, 2, false) != 0) { printf("tmap failed\n"); exit(2); }
   if constexpr (DX) CK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   else CK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   cudaEvent_t e0, e1;
@@ -85,11 +85,6 @@ static void run(int B, int H, int W, int k, int stages_cap) {
   printf("   mma-loop total cycles per CTA: min %lld  avg %.0f  max %lld  (kernel %.0f)\n", mn, s[3], mx, ms * 1e-3 * 1e9 * s[6] / s[7]);
   printf("%s k=%d cin=%d stages=%d: %.3f ms (%.0f cyc/tile at the measured clock) | per tile: mma-loop %.0f  wait_full %.0f  wait_tempty %.0f | producer wait_empty %.0f | epi wait_tfull %.0f  epi busy %.0f\n",
          DX ? "dx" : "tc", k, cin, stages, ms, ms * 1e-3 * 1e9 * (s[6] / s[7]) / tiles, s[3] / tiles, s[2] / tiles, s[1] / tiles, s[0] / tiles, s[4] / tiles, s[5] / tiles);
-  if (DX) {
-    double e[3] = {0, 0, 0};
-    for (int c = 0; c < 148; ++c) for (int i = 0; i < 3; ++i) e[i] += double(h[148 * 8 + c * 4 + i]) / 148;
-    printf("   epilogue per tile (warp 2): tmem load+wait %.0f  shuffle/sum %.0f  bias/act/store %.0f\n", e[0] / tiles, e[1] / tiles, e[2] / tiles);
-  }
   cudaFree(in_d); cudaFree(out_d); cudaFree(blob); cudaFree(prof);
 }
 

@@ -13,7 +13,7 @@
 // column-scatter conv of conv3x3_dx.cuh (TMA producer warp, tcgen05 issuer warp, 8 epilogue warps, carried
 // column sums).  Work items are strip segments (8 rows x tiles_x/segs tiles), dealt round-robin inside a group so
 // that a group always works on a compact band of strips.  A layer's epilogue warps publish "segment stored" with
-// a release-add on a per-(layer, strip) counter; the next layer's TMA producer acquires strips s-1, s, s+1 of
+// a release-add (after their TMA stores have been performed) on a per-(layer, strip) counter; the next layer's TMA producer acquires strips s-1, s, s+1 of
 // the previous layer before it requests a tile of strip s (generic-proxy writes -> async-proxy reads: the
 // acquire is followed by fence.proxy.async).  Layer 0 depends on nothing and no layer waits on a later one, so
 // with all CTAs co-resident (cooperative launch) the pipeline cannot deadlock.
@@ -74,8 +74,9 @@ conv3x3_chain_kernel(const __grid_constant__ ChainTmaps tmaps, const __grid_cons
   uint8_t* w_s = smem;
   float* bias_s = reinterpret_cast<float*>(smem + L.w_bytes);
   uint8_t* stage_s = smem + ((L.w_bytes + Cfg::kBiasBytes + 1023) & ~1023u);
-  uint8_t* out_s = stage_s + size_t(L.stages) * Cfg::kStageBytes;  // 2 staging tiles for the TMA store
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_s + 2 * Cfg::kOutTileBytes);
+  uint8_t* out_s = stage_s + size_t(L.stages) * Cfg::kStageBytes;  // per-warp staging tiles for the TMA stores
+  uint8_t* mail_s = out_s + Cfg::kOutBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mail_s + Cfg::kMailBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
@@ -124,7 +125,7 @@ conv3x3_chain_kernel(const __grid_constant__ ChainTmaps tmaps, const __grid_cons
         ptx::bulk_load(w_s + off, gsrc + off, n, w_bar);
       }
       const int* dep = li > 0 ? args.done + size_t(li - 1) * nstrips : nullptr;
-      const int dep_target = args.segs;  // one arrival per stored segment
+      const int dep_target = args.segs * kDxEpiWarps;  // one arrival per epilogue warp and stored segment
       int stage = 0;
       uint32_t phase = 0;
       long long dep_wait = 0;
@@ -196,60 +197,37 @@ conv3x3_chain_kernel(const __grid_constant__ ChainTmaps tmaps, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;
-    const int part = (warp - 2) >> 2;
-    const int prow = 2 * q + (lane >> 4);
-    const int pcol = lane & 15;
-    const bool last_col = pcol == 15;
-    const int col_w = part * Cfg::kWarpCols;
-    float carry[Cfg::kWarpCols], pend[Cfg::kWarpCols], bias_r[Cfg::kWarpCols];
-#pragma unroll
-    for (int i = 0; i < Cfg::kWarpCols; ++i) carry[i] = pend[i] = 0.f;
     ptx::mbar_wait(w_bar, 0);
-#pragma unroll
-    for (int i = 0; i < Cfg::kWarpCols; ++i) bias_r[i] = bias_s[col_w + i];
+    DxEpiWarp<KC, NT> w;
+    w.init(warp, lane, bias_s, out_s, mail_s);
     int* done = args.done + size_t(li) * nstrips;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int obuf = 0;
     long long epi_idle = 0, ntiles = 0;
     for (int item = item0; item < nitems; item += item_step) {
       const int strip = item / args.segs, seg = item - strip * args.segs;
       const int b = strip / args.tiles_y, ty = strip - b * args.tiles_y;
       const int ta = seg * args.tiles_x / args.segs, tb = (seg + 1) * args.tiles_x / args.segs;
       const int t_first = ta > 0 ? ta - 1 : ta;
-      const int y = ty * kDxTileH + prow;
       ntiles += tb - t_first;
       for (int tx = t_first; tx < tb; ++tx) {
-        const bool pre = tx < ta;
-        const bool has_pend = tx > t_first;
-        if (tx == 0) {
-#pragma unroll
-          for (int i = 0; i < Cfg::kWarpCols; ++i) carry[i] = 0.f;
-        }
-        const int x = last_col ? tx * kDxTileW - 1 : tx * kDxTileW + pcol;
-        const bool valid = (y < args.height) && (last_col ? has_pend : (!pre && x < args.width));
         const long long w0 = clock64();
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
         epi_idle += clock64() - w0;
         ptx::tc_fence_after();
-        const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::kAccCols + col_w);
-        uint8_t* out_tile = (pre || tx == 0) ? nullptr : out_s + obuf * Cfg::kOutTileBytes;  // x0 = -1 is illegal
-        dx_epilogue_tile<KC, NT>(L.epi, bias_r, t_addr, &tempty_bar[acc], carry, pend, lane, col_w, b, y, x, valid,
-                                 tx == args.tiles_x - 1, tx * kDxTileW + 15, args.height, args.width, out_tile, prow);
-        if (out_tile != nullptr) {
-          dx_store_tile(tmap_out, out_tile, warp, L.epi.out_coff, tx * kDxTileW - 1, ty * kDxTileH, b);
-          obuf ^= 1;
-        }
+        const uint32_t t_addr = tmem_base + (uint32_t(w.q * 32) << 16) + uint32_t(acc * Cfg::kAccCols);
+        dx_epilogue_tile<KC, NT>(w, L.epi, tmap_out, t_addr, &tempty_bar[acc], b, ty, tx, args.tiles_x,
+                                 /*pre=*/tx < ta, /*has_pend=*/tx > t_first, /*direct=*/false, args.height, args.width);
         if (++acc == Cfg::kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
         }
       }
-      // Publish the segment: the storing thread waits for its TMA stores to be performed, then releases.  The
-      // strip-end column (direct stores by other threads) was written before the last tile's barrier, so it is
-      // ordered before this release as well (fence cumulativity).
-      if (warp == 2 && ptx::elect_one()) {
+      // Publish this warp's share of the segment: wait until its TMA stores have been performed, then release.
+      // (Direct stores of tile 0 / the strip-end column by the other lanes are ordered before the release by the
+      // warp barrier and the cumulativity of the fence.)
+      __syncwarp();
+      if (ptx::elect_one()) {
         ptx::bulk_wait<0>();
         fence_proxy_async_all();
         __threadfence();

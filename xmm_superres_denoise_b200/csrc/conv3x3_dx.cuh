@@ -17,24 +17,30 @@
 // The +-1 column shift is applied in the epilogue.  Neighbouring columns are neighbouring TMEM lanes =
 // neighbouring threads of an epilogue warp (two image rows of 16 columns per warp): two warp shuffles per
 // output value.  Across the 16-column tile boundary the sums are CARRIED: a CTA walks a strip of 8 image
-// rows left to right, lane 15 of each row keeps D_0[15] (the left term of the next tile's column 0) and the
-// unfinished sum D_0[14] + D_1[15] of its own column, which it completes -- and stores -- one tile later when
-// lane 0 holds D_2[16].  No column halo is ever loaded or multiplied: every MMA row is a useful pixel
-// (D_0[-1] and D_2[W] are products with the zero padding).
+// rows left to right; lane 15 of each row leaves D_0[15] (the left term of the next tile's column 0) and the
+// unfinished sum D_0[14] + D_1[15] of its own column in a per-warp shared-memory mailbox and completes -- and
+// stores -- that column one tile later, when lane 0 holds D_2[16].  No column halo is ever loaded or multiplied:
+// every MMA row is a useful pixel (D_0[-1] and D_2[W] are products with the zero padding).  The mailbox moves
+// are predicated 16-byte shared-memory accesses of the two boundary lanes, so the common path has no selects.
 //
-// Work split: the B * ceil(H/8) * ceil(W/16) tiles, strip-major, are cut into gridDim.x equal contiguous
-// ranges.  A range that starts mid-strip first runs the tile before it as a "pre-tile" (outputs suppressed)
-// to establish the carry; a range that ends mid-strip leaves its last column to the next CTA's pre-tile.
+// Work split.  Large problems (>= 4 strips per CTA): whole strips are dealt round-robin, so that at any moment the
+// CTAs work on a band of ADJACENT strips at about the same column -- the two halo rows a strip shares with its
+// neighbours are then read from L2 instead of HBM (measured: with contiguous ranges the halo was re-read from
+// DRAM, 1.25x the algorithmic traffic, and the kernel is DRAM-bound for cin >= 96).  Small problems: the
+// B * ceil(H/8) * ceil(W/16) tiles, strip-major, are cut into gridDim.x equal contiguous ranges; a range that
+// starts mid-strip first runs the tile before it as a "pre-tile" (outputs suppressed) to establish the carry, a
+// range that ends mid-strip leaves its last column to the next CTA's pre-tile.
 //
-// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..17 = epilogue:
-// TMEM lane quarter = warp_id % 4, and the four warps of a quarter take a quarter of the Cout columns each.  The
-// epilogue is ~20 dependent instructions per output value (measured: latency-bound with 2 warps per scheduler),
-// so it is spread over 4 warps per scheduler to keep up with the MMAs of the narrow layers.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue:
+// TMEM lane quarter = warp_id % 4, and the two warps of a quarter take half of the Cout columns each.  Every
+// epilogue warp stages its [2 rows][16 px][Cout/2] result in its own swizzled shared-memory tile and issues its
+// own TMA store (box x = 16*tx - 1: the carried column comes first; rows / columns outside the image are clipped
+// by the tensor map), so the epilogue warps never synchronise with each other.  A TMA store may not start at a
+// negative coordinate (illegal instruction on B200), so tile 0 of a strip stores directly.
 //
-// Everything else -- resident weights, TMA pipeline, double-buffered TMEM accumulators, fused
-// bias / LeakyReLU / mask / residual / inverse-pixel-shuffle epilogue -- is conv3x3_tc.cuh's.
-// The packed weight image is the same one ([chunk][tap][Cout][KC]: the three dx taps of a row
-// are adjacent, so they are one N = 3*Cout operand).
+// Everything else -- resident weights, TMA pipeline, TMEM accumulator ring, fused bias / LeakyReLU / mask /
+// residual / inverse-pixel-shuffle arithmetic -- is conv3x3_tc.cuh's.  The packed weight image is the same one
+// ([chunk][tap][Cout][KC]: the three dx taps of a row are adjacent, so they are one N = 3*Cout operand).
 #pragma once
 #include "conv3x3_tc.cuh"
 
@@ -43,7 +49,7 @@ namespace xmm {
 constexpr int kDxTileH = 8;
 constexpr int kDxTileW = 16;
 constexpr int kDxPatchH = kDxTileH + 2;
-constexpr int kDxEpiWarps = 16;
+constexpr int kDxEpiWarps = 8;
 constexpr int kDxThreads = 64 + 32 * kDxEpiWarps;
 
 template <int KC, int NT>
@@ -61,23 +67,50 @@ struct DxCfg {
   static constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, 3 * NT, 0, 0);
   static constexpr int kBiasBytes = NT * 4;
   static constexpr int kBarBytes = (2 * kMaxStages + 2 * 4 + 1) * 8 + 16;
-  static constexpr int kWarpCols = NT / 4;          // Cout columns owned by one epilogue warp
-  static constexpr int kChunk = kWarpCols < 16 ? kWarpCols : 16;  // columns per tcgen05.ld / store group
-  static constexpr int kWarpChunks = kWarpCols / kChunk;
-  static constexpr int kOutRowB = NT * 2;                          // one output pixel in the store staging tile
-  static constexpr int kOutTileBytes = kDxTileH * kDxTileW * kOutRowB;  // 8 KB / 16 KB, [8][16] pixels, TMA swizzled
+  static constexpr int kWarpCols = NT / 2;          // Cout columns owned by one epilogue warp
+  static constexpr int kWarpChunks = kWarpCols / 16;  // 16-column groups per tcgen05.ld / arithmetic pass
+  // per-warp output staging tile for the TMA store: [2 rows][16 px] x kWarpCols bf16, swizzled (32 B / 64 B rows)
+  static constexpr int kWarpOutBytes = 32 * kWarpCols * 2;
+  static constexpr int kOutBytes = kDxEpiWarps * 2 * kWarpOutBytes;  // double buffered
+  // per-warp carry mailboxes: [parity][A = D_0 of column 15 | B = unfinished column 15][half-warp row][kWarpCols] fp32
+  static constexpr int kWarpMailBytes = 2 * 2 * 2 * kWarpCols * 4;
+  static constexpr int kMailBytes = kDxEpiWarps * kWarpMailBytes;
   static size_t smem_bytes(uint32_t w_bytes, int stages) {
-    return 1024 + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + 2 * kOutTileBytes + kBarBytes;
+    return 1024 + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kOutBytes + kMailBytes + kBarBytes;
   }
 };
 
-// Byte offset of 16-byte chunk k16 of pixel p inside a staging tile whose rows are 64 B (SWIZZLE_64B: chunk bits
-// [4,6) ^= address bits [7,9)) or 128 B (SWIZZLE_128B: chunk bits [4,7) ^= address bits [7,10)) -- the layout the
-// output tensor map expects, and conflict-free for a warp's 16-byte stores.
+// Byte offset of 16-byte chunk k16 of warp-local pixel p (0..31) inside a warp's staging tile: rows of 32 B
+// (SWIZZLE_32B: chunk bit 4 ^= address bit 7) or 64 B (SWIZZLE_64B: chunk bits [4,6) ^= address bits [7,9)) --
+// the layout the output tensor map expects, and conflict-free for the warp's 16-byte stores.
 template <int NT>
 __device__ __forceinline__ uint32_t dx_out_offset(int p, int k16) {
-  if (NT == 32) return uint32_t(p * 64 + ((k16 ^ ((p >> 1) & 3)) << 4));
-  return uint32_t(p * 128 + ((k16 ^ (p & 7)) << 4));
+  if (NT == 32) return uint32_t(p * 32 + ((k16 ^ ((p >> 2) & 1)) << 4));
+  return uint32_t(p * 64 + ((k16 ^ ((p >> 1) & 3)) << 4));
+}
+
+// Predicated 16-byte shared-memory moves IN PLACE (the boundary lanes' mailbox traffic must not turn into a
+// select per value on the other 30 lanes).
+__device__ __forceinline__ void lds4_if(bool p, float& a, float& b, float& c, float& d, uint32_t addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%5];\n\t"
+      "}\n"
+      : "+f"(a), "+f"(b), "+f"(c), "+f"(d)
+      : "r"(int(p)), "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void sts4_if(bool p, float a, float b, float c, float d, uint32_t addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q st.shared.v4.f32 [%5], {%0, %1, %2, %3};\n\t"
+      "}\n" ::"f"(a),
+      "f"(b), "f"(c), "f"(d), "r"(int(p)), "r"(addr)
+      : "memory");
 }
 
 // Tile g of the strip-major order -> image, strip row, tile column.
@@ -115,103 +148,146 @@ __device__ __forceinline__ void dx_issue_chunk(uint32_t d_addr, uint64_t adesc_s
   }
 }
 
-// Epilogue of one tile for one warp: read this warp's columns of the three partial sums, form
-// out[c] = D_0[c-1] + D_1[c] + D_2[c+1] with two shuffles (the tile-boundary terms come from / go to the
-// carry registers of lane 15 of each row), release the accumulator, apply the fused epilogue and store.
-// `x` is this lane's output column: the current tile's for lanes 0..14, the previous tile's column 15 for lane 15.
+// Per-warp constants of the epilogue.
 template <int KC, int NT>
-__device__ __forceinline__ void dx_epilogue_tile(const ConvEpilogue& epi,
-                                                 const float (&bias_r)[NT / 4], uint32_t t_addr, uint64_t* tempty,
-                                                 float (&carry)[NT / 4], float (&pend)[NT / 4], int lane, int col_w, int b, int y, int x,
-                                                 bool valid, bool strip_end, int flush_x, int H, int W,
-                                                 uint8_t* out_tile,  // != nullptr: stage for a TMA store
-                                                 int prow            // this lane's row inside the tile
-#ifdef XMM_CONV_PROFILE
-                                                 , long long* pa
-#endif
-                                                 ) {
+struct DxEpiWarp {
   using Cfg = DxCfg<KC, NT>;
-#ifdef XMM_CONV_PROFILE
-  long long pt = clock64(), pn;
-#define XMM_EPI_MARK(i) pn = clock64(); pa[i] += pn - pt; pt = pn
-#else
-#define XMM_EPI_MARK(i)
-#endif
-  const bool last_col = (lane & 15) == 15;
-  const int src_l = (lane & 16) | ((lane + 15) & 15);
-  const int src_r = (lane & 16) | ((lane + 1) & 15);
-  constexpr int CH = Cfg::kChunk;
+  int lane, q, half, prow, pcol, col_w;
+  bool first_col, last_col;
+  int src_l, src_r;
+  uint32_t mail;       // shared-memory address of this warp's mailboxes (+ this lane's half-warp row)
+  uint8_t* out_tile;   // this warp's two staging tiles
+  float bias[Cfg::kWarpCols];
+  int par;             // tile parity (mailbox / staging double buffering)
+  __device__ __forceinline__ void init(int warp, int lane_, const float* bias_s, uint8_t* out_s, uint8_t* mail_s) {
+    lane = lane_;
+    q = warp & 3;
+    half = (warp - 2) >> 2;
+    prow = 2 * q + (lane >> 4);
+    pcol = lane & 15;
+    first_col = pcol == 0;
+    last_col = pcol == 15;
+    src_l = (lane & 16) | ((lane + 15) & 15);
+    src_r = (lane & 16) | ((lane + 1) & 15);
+    col_w = half * Cfg::kWarpCols;
+    const int ew = warp - 2;
+    mail = ptx::smem_u32(mail_s + ew * Cfg::kWarpMailBytes) + uint32_t((lane >> 4) * Cfg::kWarpCols * 4);
+    out_tile = out_s + ew * 2 * Cfg::kWarpOutBytes;
+    par = 0;
+#pragma unroll
+    for (int i = 0; i < Cfg::kWarpCols; ++i) bias[i] = bias_s[col_w + i];
+  }
+  // mailbox slot: kind 0 = D_0 of column 15, kind 1 = unfinished column 15
+  __device__ __forceinline__ uint32_t slot(int parity, int kind) const {
+    return mail + uint32_t((parity * 2 + kind) * 2 * Cfg::kWarpCols * 4);
+  }
+};
+
+// Epilogue of one tile for one warp.  Reads this warp's columns of the three partial sums, forms
+// out[c] = D_0[c-1] + D_1[c] + D_2[c+1] with two shuffles per value (tile-boundary terms through the mailbox),
+// releases the accumulator, applies the fused arithmetic and stores (TMA store through the warp's staging tile, or
+// directly when `direct`).  Lanes 0..14 own columns 16*tx + lane of the current tile, lane 15 the previous
+// tile's column 15.
+//   tx          tile column inside the strip (0: no left neighbour; the mailbox is not read)
+//   pre         pre-tile: only the carry is produced
+//   has_pend    lane 15 holds an unfinished column from the previous tile of this CTA
+template <int KC, int NT>
+__device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const ConvEpilogue& epi,
+                                                 const CUtensorMap* tmap_out, uint32_t t_addr, uint64_t* tempty, int b,
+                                                 int ty, int tx, int tiles_x, bool pre, bool has_pend, bool direct, int H,
+                                                 int W) {
+  using Cfg = DxCfg<KC, NT>;
+  const int y = ty * kDxTileH + w.prow;
+  const int x = w.last_col ? tx * kDxTileW - 1 : tx * kDxTileW + w.pcol;
+  const bool valid = (y < H) && (w.last_col ? has_pend : (!pre && x < W));
+  const bool strip_end = (tx == tiles_x - 1) && !pre;
+  const bool use_tma = !direct && !pre && tx > 0;
+  uint8_t* stage = w.out_tile + w.par * Cfg::kWarpOutBytes;
+  if (use_tma) {  // the TMA store issued two tiles ago has finished reading this staging tile
+    if (ptx::elect_one()) ptx::bulk_wait_read<1>();
+    __syncwarp();
+  }
 #pragma unroll
   for (int cc = 0; cc < Cfg::kWarpChunks; ++cc) {
-    uint32_t d0[CH], d1[CH], d2[CH];
-    ptx::tmem_ld_cols<CH>(t_addr + uint32_t(cc * CH), d0);
-    ptx::tmem_ld_cols<CH>(t_addr + uint32_t(NT + cc * CH), d1);
-    ptx::tmem_ld_cols<CH>(t_addr + uint32_t(2 * NT + cc * CH), d2);
+    uint32_t d0[16], d1[16], d2[16];
+    const uint32_t ta = t_addr + uint32_t(w.col_w + cc * 16);
+    ptx::tmem_ld_32x16(ta, d0);
+    ptx::tmem_ld_32x16(ta + uint32_t(NT), d1);
+    ptx::tmem_ld_32x16(ta + uint32_t(2 * NT), d2);
     ptx::tmem_ld_wait();
-    XMM_EPI_MARK(0);
     if (cc == Cfg::kWarpChunks - 1) {
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty);
+      if (w.lane == 0) ptx::mbar_arrive(tempty);
     }
-    float v[CH];
+    const uint32_t a_w = w.slot(w.par, 0) + uint32_t(cc * 64), a_r = w.slot(w.par ^ 1, 0) + uint32_t(cc * 64);
+    const uint32_t b_w = w.slot(w.par, 1) + uint32_t(cc * 64), b_r = w.slot(w.par ^ 1, 1) + uint32_t(cc * 64);
+    // lane 15 publishes D_0[15] for the next tile's lane 0
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const float c0 = __uint_as_float(d0[i]);
-      const float send = last_col ? carry[cc * CH + i] : c0;
+    for (int j = 0; j < 4; ++j)
+      sts4_if(w.last_col, __uint_as_float(d0[4 * j]), __uint_as_float(d0[4 * j + 1]), __uint_as_float(d0[4 * j + 2]),
+              __uint_as_float(d0[4 * j + 3]), a_w + uint32_t(j * 16));
+    float left[16], right[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
 #ifdef XMM_EXP_NOSHFL
-      const float left = send, right = __uint_as_float(d2[i]);
+      left[i] = __uint_as_float(d0[i]);
+      right[i] = __uint_as_float(d2[i]);
 #else
-      const float left = __shfl_sync(0xffffffffu, send, src_l);
-      const float right = __shfl_sync(0xffffffffu, __uint_as_float(d2[i]), src_r);
+      left[i] = __shfl_sync(0xffffffffu, __uint_as_float(d0[i]), w.src_l);
+      right[i] = __shfl_sync(0xffffffffu, __uint_as_float(d2[i]), w.src_r);
 #endif
-      const float lsum = left + (__uint_as_float(d1[i]) + bias_r[cc * CH + i]);
-      v[i] = (last_col ? pend[cc * CH + i] : lsum) + right;
-      pend[cc * CH + i] = lsum;   // meaningful on lane 15 only: D_0[14] + D_1[15] (+ bias)
-      carry[cc * CH + i] = c0;    // meaningful on lane 15 only: D_0[15]
     }
-    XMM_EPI_MARK(1);
-    if (out_tile != nullptr) {
-      if (valid) {
-        conv_epilogue_math<NT, CH>(epi, nullptr, v, col_w + cc * CH, b, y, x, H, W);
-        // box pixel: image row of this lane, column = lane column + 1 (lane 15 is the box's column 0)
-        const int p = prow * kDxTileW + (((lane & 15) + 1) & 15);
+    // lane 0: its left neighbour is the previous tile's column 15 (strip start: the zero padding)
+    if (tx == 0) {
 #pragma unroll
-        for (int j = 0; j < CH / 8; ++j)
-          *reinterpret_cast<uint4*>(out_tile + dx_out_offset<NT>(p, (col_w + cc * CH) / 8 + j)) = pack8(v + j * 8);
+      for (int i = 0; i < 16; ++i) left[i] = w.first_col ? 0.f : left[i];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        lds4_if(w.first_col, left[4 * j], left[4 * j + 1], left[4 * j + 2], left[4 * j + 3], a_r + uint32_t(j * 16));
+    }
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = left[i] + (__uint_as_float(d1[i]) + w.bias[cc * 16 + i]);
+    // lane 15: park D_0[14] + D_1[15] (+ bias) of this tile, take over the previous tile's parked column
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sts4_if(w.last_col, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], b_w + uint32_t(j * 16));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lds4_if(w.last_col, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], b_r + uint32_t(j * 16));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += right[i];
+    const int col = w.col_w + cc * 16;
+    if (valid) {
+      if (use_tma) {
+        conv_epilogue_math<NT, 16>(epi, nullptr, v, col, b, y, x, H, W);
+        const int p = (w.lane >> 4) * kDxTileW + ((w.pcol + 1) & 15);  // box pixel: lane 15 is the box's column 0
+        *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2)) = pack8(v);
+        *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2 + 1)) = pack8(v + 8);
+      } else {
+        conv_epilogue_cols<NT, 16>(epi, nullptr, v, col, b, y, x, H, W);
       }
-    } else if (valid) {
-      conv_epilogue_cols<NT, CH>(epi, nullptr, v, col_w + cc * CH, b, y, x, H, W);
     }
-    XMM_EPI_MARK(2);
-  }
-  // End of the strip: column 15 of the last tile has no right neighbour (D_2[W] = 0).
-  if (strip_end && last_col && y < H && flush_x < W) {
+    // End of the strip: column 15 of the last tile has no right neighbour (D_2[W] = 0).
+    if (strip_end && w.last_col && y < H && tx * kDxTileW + 15 < W) {
+      float f[16];
 #pragma unroll
-    for (int cc = 0; cc < Cfg::kWarpChunks; ++cc) {
-      float v[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) v[i] = pend[cc * CH + i];
-      conv_epilogue_cols<NT, CH>(epi, nullptr, v, col_w + cc * CH, b, y, flush_x, H, W);
+      for (int j = 0; j < 4; ++j) {
+        const float4 t4 = *reinterpret_cast<const float4*>(__cvta_shared_to_generic(size_t(b_w) + size_t(j * 16)));
+        f[4 * j] = t4.x; f[4 * j + 1] = t4.y; f[4 * j + 2] = t4.z; f[4 * j + 3] = t4.w;
+      }
+      conv_epilogue_cols<NT, 16>(epi, nullptr, f, col, b, y, tx * kDxTileW + 15, H, W);
     }
   }
-}
-
-// After every epilogue warp has staged its part of a tile: one TMA store of the [8][16]-pixel x NT-channel box
-// whose column 0 is the previous tile's column 15 (box x = 16*tx - 1; out-of-image rows / columns are clipped by
-// the tensor map on the high side, which is what makes the carried column and the ragged edges free; the box may
-// not start below 0, so tile 0 of a strip uses direct stores instead).  Called by all epilogue
-// warps.  The staging tile is double buffered: the elected thread first makes sure the store issued two tiles ago
-// has finished reading this buffer (it waits for the reads of all its earlier stores; they are a tile old).
-__device__ __forceinline__ void dx_store_tile(const CUtensorMap* tmap_out, const uint8_t* out_tile, int warp, int c0,
-                                              int x0, int y0, int b) {
-  ptx::fence_proxy_async();  // this thread's st.shared -> visible to the async proxy
-  if (warp == 2 && ptx::elect_one()) ptx::bulk_wait_read<0>();
-  ptx::named_bar_sync(1, 32 * kDxEpiWarps);
-  if (warp == 2 && ptx::elect_one()) {
-    ptx::tma_store_4d(tmap_out, out_tile, c0, x0, y0, b);
-    ptx::bulk_commit();
+  if (use_tma) {
+    ptx::fence_proxy_async();  // this thread's st.shared -> visible to the async proxy
+    __syncwarp();
+    if (ptx::elect_one()) {
+      ptx::tma_store_4d(tmap_out, stage, epi.out_coff + w.col_w, tx * kDxTileW - 1, ty * kDxTileH + 2 * w.q, b);
+      ptx::bulk_commit();
+    }
   }
+  w.par ^= 1;
 }
 
 template <int KC, int NT>
@@ -224,8 +300,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   uint8_t* w_s = smem;
   float* bias_s = reinterpret_cast<float*>(smem + args.w_bytes);
   uint8_t* stage_s = smem + ((args.w_bytes + Cfg::kBiasBytes + 1023) & ~1023u);
-  uint8_t* out_s = stage_s + size_t(args.stages) * Cfg::kStageBytes;  // 2 staging tiles for the TMA store
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_s + 2 * Cfg::kOutTileBytes);
+  uint8_t* out_s = stage_s + size_t(args.stages) * Cfg::kStageBytes;  // per-warp staging tiles for the TMA stores
+  uint8_t* mail_s = out_s + Cfg::kOutBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mail_s + Cfg::kMailBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
@@ -238,7 +315,6 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 #ifdef XMM_CONV_PROFILE
   long long prof_t0_ = 0;
   long long prof_acc_[6] = {0, 0, 0, 0, 0, 0};
-  long long prof_epi_[3] = {0, 0, 0};
   const long long prof_k0_ = clock64();
   unsigned long long prof_g0_;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_g0_));
@@ -264,11 +340,16 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  // This CTA's contiguous tile range [t0, t1) of the strip-major order; g0 < t0 adds the pre-tile.
+  // This CTA's tiles: runs of consecutive tiles [g, run_end) of the strip-major order.  Contiguous mode: one run
+  // [t0, t1) (+ the pre-tile g0 = t0 - 1 when it starts mid-strip).  Round-robin mode: one run per strip
+  // blockIdx.x, blockIdx.x + gridDim.x, ...
   const long long total = args.num_tiles;
-  const int t0 = int(total * blockIdx.x / gridDim.x);
-  const int t1 = int(total * (blockIdx.x + 1) / gridDim.x);
-  const int g0 = (t0 % args.tiles_x != 0) ? t0 - 1 : t0;
+  const bool rr = args.strip_rr != 0;
+  const int t0 = rr ? int(blockIdx.x) * args.tiles_x : int(total * blockIdx.x / gridDim.x);
+  const int t1 = rr ? int(total) : int(total * (blockIdx.x + 1) / gridDim.x);
+  const int g0 = (!rr && t0 % args.tiles_x != 0) ? t0 - 1 : t0;
+  const int run_len = rr ? args.tiles_x : (t1 - g0);                 // tiles per run
+  const int run_step = rr ? int(gridDim.x) * args.tiles_x : (t1 - g0 > 0 ? t1 - g0 : 1);  // distance between runs
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -282,19 +363,21 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       }
       int stage = 0;
       uint32_t phase = 0;
-      DxTile t(g0, args.tiles_x, args.tiles_y);
-      for (int g = g0; g < t1; ++g, t.next(args.tiles_x, args.tiles_y)) {
-        const int y0 = t.ty * kDxTileH - 1, x0 = t.tx * kDxTileW;
-        for (int ch = 0; ch < args.nchunks; ++ch) {
-          XMM_PROF_T0();
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          XMM_PROF_ADD(0);
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          ptx::tma_load_4d(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in, &full_bar[stage],
-                           args.cin_off + ch * KC, x0, y0, t.b);
-          if (++stage == args.stages) {
-            stage = 0;
-            phase ^= 1u;
+      for (int r0 = g0; r0 < t1; r0 += run_step) {
+        DxTile t(r0, args.tiles_x, args.tiles_y);
+        for (int g = r0; g < r0 + run_len; ++g, t.next(args.tiles_x, args.tiles_y)) {
+          const int y0 = t.ty * kDxTileH - 1, x0 = t.tx * kDxTileW;
+          for (int ch = 0; ch < args.nchunks; ++ch) {
+            XMM_PROF_T0();
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            XMM_PROF_ADD(0);
+            ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            ptx::tma_load_4d(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in, &full_bar[stage],
+                             args.cin_off + ch * KC, x0, y0, t.b);
+            if (++stage == args.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -314,7 +397,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       XMM_PROF_START(3);
-      for (int g = g0; g < t1; ++g) {
+      int my_tiles = 0;
+      for (int r0 = g0; r0 < t1; r0 += run_step) my_tiles += run_len;
+      for (int g = 0; g < my_tiles; ++g) {
         XMM_PROF_T0();
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         XMM_PROF_ADD(1);
@@ -345,65 +430,33 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;                   // TMEM lane quarter = image rows 2q, 2q+1 of the strip
-    const int part = (warp - 2) >> 2;         // which quarter of the Cout columns
-    const int prow = 2 * q + (lane >> 4);
-    const int pcol = lane & 15;
-    const bool last_col = pcol == 15;         // finishes the PREVIOUS tile's column 15
-    const int col_w = part * Cfg::kWarpCols;
-    float carry[Cfg::kWarpCols], pend[Cfg::kWarpCols], bias_r[Cfg::kWarpCols];
-#pragma unroll
-    for (int i = 0; i < Cfg::kWarpCols; ++i) carry[i] = pend[i] = 0.f;
     ptx::mbar_wait(w_bar, 0);
-#pragma unroll
-    for (int i = 0; i < Cfg::kWarpCols; ++i) bias_r[i] = bias_s[col_w + i];
+    DxEpiWarp<KC, NT> w;
+    w.init(warp, lane, bias_s, out_s, mail_s);
+    const bool direct = args.epi.pixel_shuffle != 0;  // (inverse) pixel shuffle scatters: direct stores
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool use_tma = args.epi.pixel_shuffle == 0;  // (inverse) pixel shuffle scatters: direct stores
-    int obuf = 0;
-    DxTile t(g0, args.tiles_x, args.tiles_y);  // advanced incrementally: no divisions in the tile loop
-    for (int g = g0; g < t1; ++g) {
-      const int y = t.ty * kDxTileH + prow;
-      const bool pre = g < t0;
-      const bool has_pend = (t.tx > 0) && (g != g0);
-      if (t.tx == 0) {
-#pragma unroll
-        for (int i = 0; i < Cfg::kWarpCols; ++i) carry[i] = 0.f;  // D_0[-1]: zero padding
+    for (int r0 = g0; r0 < t1; r0 += run_step) {
+      DxTile t(r0, args.tiles_x, args.tiles_y);  // advanced incrementally: no divisions in the tile loop
+      for (int g = r0; g < r0 + run_len; ++g) {
+        XMM_PROF_T0();
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        XMM_PROF_ADD(4);
+        XMM_PROF_T0();
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t(w.q * 32) << 16) + uint32_t(acc * Cfg::kAccCols);
+        dx_epilogue_tile<KC, NT>(w, args.epi, &tmap_out, t_addr, &tempty_bar[acc], t.b, t.ty, t.tx, args.tiles_x,
+                                 /*pre=*/g < t0, /*has_pend=*/(t.tx > 0) && (g != r0), direct, args.height, args.width);
+        XMM_PROF_ADD(5);
+        if (++acc == Cfg::kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        t.next(args.tiles_x, args.tiles_y);
       }
-      const int x = last_col ? t.tx * kDxTileW - 1 : t.tx * kDxTileW + pcol;
-      const bool valid = (y < args.height) && (last_col ? has_pend : (!pre && x < args.width));
-      XMM_PROF_T0();
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      XMM_PROF_ADD(4);
-      XMM_PROF_T0();
-      ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * Cfg::kAccCols + col_w);
-      // a TMA store may not start at a negative coordinate (x = -1 is an illegal instruction on B200): the first
-      // tile of a strip, whose box column 0 is outside the image anyway, stores directly
-      uint8_t* out_tile = (use_tma && !pre && t.tx > 0) ? out_s + obuf * Cfg::kOutTileBytes : nullptr;
-      dx_epilogue_tile<KC, NT>(args.epi, bias_r, t_addr, &tempty_bar[acc], carry, pend, lane, col_w, t.b, y, x, valid,
-                               t.tx == args.tiles_x - 1, t.tx * kDxTileW + 15, args.height, args.width, out_tile, prow
-#ifdef XMM_CONV_PROFILE
-                               , prof_epi_
-#endif
-                               );
-      if (out_tile != nullptr) {
-        dx_store_tile(&tmap_out, out_tile, warp, args.epi.out_coff, t.tx * kDxTileW - 1, t.ty * kDxTileH, t.b);
-        obuf ^= 1;
-      }
-      XMM_PROF_ADD(5);
-      if (++acc == Cfg::kAccStages) {
-        acc = 0;
-        acc_phase ^= 1u;
-      }
-      t.next(args.tiles_x, args.tiles_y);
     }
-    if (warp == 2 && ptx::elect_one()) ptx::bulk_wait<0>();  // stores complete before the CTA (and its smem) goes away
+    if (ptx::elect_one()) ptx::bulk_wait<0>();  // this warp's stores complete before the CTA (and its smem) goes away
     if (warp == 2 && lane == 0) { XMM_PROF_FLUSH(4); XMM_PROF_FLUSH(5); }
-#ifdef XMM_CONV_PROFILE
-    if (warp == 2 && lane == 0)
-      for (int i = 0; i < 3; ++i) args.prof[size_t(gridDim.x) * 8 + size_t(blockIdx.x) * 4 + i] = prof_epi_[i];
-#endif
   }
 
   ptx::tc_fence_before();

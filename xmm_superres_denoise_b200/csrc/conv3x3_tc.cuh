@@ -79,6 +79,7 @@ struct ConvArgs {
   int batch, height, width;
   int tiles_x, tiles_y, num_tiles;
   int stages;
+  int strip_rr;  // conv3x3_dx: 1 = whole strips dealt round-robin to the CTAs, 0 = equal contiguous tile ranges
   ConvEpilogue epi;
 #ifdef XMM_CONV_PROFILE
   long long* prof;  // [gridDim.x][8] cycle counters (tools/probe.cu only)
@@ -389,6 +390,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
         }
+#ifdef XMM_EXP_NOEPI
+        if (__uint_as_float(accr[0]) == 123.456f)
+#endif
         if (valid) conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
       }
       XMM_PROF_ADD(5);

@@ -164,7 +164,7 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   if (rc != XMM_OK) return rc;
   CUtensorMap tmap_out = tmap;  // unused (direct stores) when the output is pixel-shuffled
   if (p.pixel_shuffle == 0) {
-    rc = cached_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, NT, kDxTileW, kDxTileH);
+    rc = cached_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, Cfg::kWarpCols, kDxTileW, 2);
     if (rc != XMM_OK) return rc;
   }
   static bool attr_set = false;
@@ -174,6 +174,11 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
     attr_set = true;
   }
   const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
+  // >= 4 strips per CTA: deal whole strips round-robin (halo rows of adjacent strips meet in L2); XMM_DX_RR=0/1 forces
+  static const int rr_env = [] { const char* e = getenv("XMM_DX_RR"); return e ? atoi(e) : -1; }();
+  const long long nstrips = (long long)a.tiles_y * p.batch;
+  // (cin <= 64 is not DRAM-bound: there the round-robin's wave quantisation only pays off with many strips)
+  a.strip_rr = rr_env >= 0 ? (rr_env != 0) : (nstrips >= 4LL * grid && (a.nchunks >= 3 || nstrips >= 16LL * grid));
   conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
@@ -366,7 +371,7 @@ int launch_chain(const xmm_conv3x3_params* L, int n, const DeviceInfo& dev, int*
     fill_epilogue(c.epi, L[l]);
     int rc = cached_tmap(&tm.m[l], L[l].in, a.batch, a.height, a.width, L[l].in_ctot, 32, kDxTileW, kDxPatchH);
     if (rc != XMM_OK) return rc;
-    rc = cached_tmap(&tm.out[l], L[l].out, a.batch, a.height, a.width, L[l].out_ctot, 32, kDxTileW, kDxTileH);
+    rc = cached_tmap(&tm.out[l], L[l].out, a.batch, a.height, a.width, L[l].out_ctot, Cfg::kWarpCols, kDxTileW, 2);
     if (rc != XMM_OK) return rc;
   }
   const int total_ctas = begin;
