@@ -25,9 +25,14 @@
 namespace xmm {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgStages = 2;
-constexpr int kWgBoxXBytes = 23552;   // 18*10 pixels * 128 B = 23040, padded to a 1024-B multiple
-constexpr int kWgBoxYBytes = 16384;   // 16*8 pixels * 128 B
+// Pixel tile of one pipeline stage: 8 rows x 8 columns (4 MMAs of K = 16 pixels per tap), which lets 4 stages fit
+// (a 16-row tile is 95 KB per stage: only two).  Measured on B200 (ncu, dense block at batch 16): 1.15 ms, tensor
+// pipe 59 % active, DRAM 30 %, L2 28 % with EITHER tile height -- the limiter is not the pipeline depth but the
+// per-instruction cost of the MN-major tap views (A starts at arbitrary 128-byte rows of the swizzle atom).
+constexpr int kWgTileH = 8;
+constexpr int kWgMaxStages = 6;
+constexpr int kWgBoxXBytes = 13312;   // (8+2)*10 pixels * 128 B = 12800, padded to a 1024-B multiple
+constexpr int kWgBoxYBytes = 8192;    // 8*8 pixels * 128 B
 constexpr int kWgMaxRoles = 4;
 constexpr int kWgWsFloatsPerCta = 128 * 512;
 
@@ -46,6 +51,7 @@ struct WgradArgs {
   int nroles;
   int batch, height, width;
   int tiles_x, tiles_y, num_tiles;
+  int stages;    // pipeline depth (<= kWgMaxStages)
   float* ws;     // [gridDim.x][128 lanes][512 columns] fp32 partial sums
 };
 
@@ -54,7 +60,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 const WgradArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kWgStages], empty_bar[kWgStages], done_bar;
+  __shared__ uint64_t full_bar[kWgMaxStages], empty_bar[kWgMaxStages], done_bar;
   __shared__ uint32_t tmem_ptr_s;
 
   const int warp = threadIdx.x >> 5;
@@ -72,7 +78,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_y);
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < args.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
@@ -96,16 +102,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int ty = r / args.tiles_x;
         const int tx = r - ty * args.tiles_x;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-        ptx::mbar_expect_tx(&full_bar[stage], uint32_t(role.x_boxes * 18 * 10 * 128 + role.y_boxes * kWgBoxYBytes));
+        ptx::mbar_expect_tx(&full_bar[stage], uint32_t(role.x_boxes * (kWgTileH + 2) * (kTileW + 2) * 128 + role.y_boxes * kWgBoxYBytes));
         uint8_t* dst = smem + size_t(stage) * stage_bytes;
         for (int xb = 0; xb < role.x_boxes; ++xb)
           ptx::tma_load_4d(dst + xb * kWgBoxXBytes, &tmap_x, &full_bar[stage], role.x_c0 + 64 * xb, tx * kTileW - 1,
-                           ty * kTileH - 1, b);
+                           ty * kWgTileH - 1, b);
         uint8_t* ydst = dst + role.x_boxes * kWgBoxXBytes;
         for (int yb = 0; yb < role.y_boxes; ++yb)
           ptx::tma_load_4d(ydst + yb * kWgBoxYBytes, &tmap_y, &full_bar[stage], role.y_c0 + 64 * yb, tx * kTileW,
-                           ty * kTileH, b);
-        if (++stage == kWgStages) {
+                           ty * kWgTileH, b);
+        if (++stage == args.stages) {
           stage = 0;
           phase ^= 1u;
         }
@@ -124,7 +130,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const uint32_t x_addr = ptx::smem_u32(smem + size_t(stage) * stage_bytes);
         const uint32_t y_addr = x_addr + uint32_t(role.x_boxes * kWgBoxXBytes);
 #pragma unroll 1
-        for (int s = 0; s < kTileH / 2; ++s) {  // 16 pixels (two tile rows) per MMA
+        for (int s = 0; s < kWgTileH / 2; ++s) {  // 16 pixels (two tile rows) per MMA
           const uint64_t bdesc = ptx::umma_smem_desc(y_addr + uint32_t(s * 2 * kTileW * 128), kWgBoxYBytes,
                                                      kTileW * 128, ptx::UMMA_SW128);
 #pragma unroll 1
@@ -138,7 +144,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
         first = false;
         ptx::umma_commit(&empty_bar[stage]);
-        if (++stage == kWgStages) {
+        if (++stage == args.stages) {
           stage = 0;
           phase ^= 1u;
         }

@@ -679,11 +679,14 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   }
   a.batch = p.batch; a.height = p.height; a.width = p.width;
   a.tiles_x = (p.width + kTileW - 1) / kTileW;
-  a.tiles_y = (p.height + kTileH - 1) / kTileH;
+  a.tiles_y = (p.height + kWgTileH - 1) / kWgTileH;
   a.num_tiles = a.tiles_x * a.tiles_y * p.batch;
   a.ws = p.workspace;
-  const size_t smem = 1024 + kWgStages * max_stage;
-  XMM_REQUIRE(smem <= size_t(dev.max_smem_optin - 1024), "wgrad: stage of %zu B does not fit twice in shared memory", max_stage);
+  int wg_stages = int((size_t(dev.max_smem_optin) - 2048) / max_stage);
+  if (wg_stages > kWgMaxStages) wg_stages = kWgMaxStages;
+  XMM_REQUIRE(wg_stages >= 2, "wgrad: stage of %zu B does not fit twice in shared memory", max_stage);
+  a.stages = wg_stages;
+  const size_t smem = 1024 + size_t(wg_stages) * max_stage;
 
   ra.ws = p.workspace;
   ra.ndst = p.ndst;
@@ -699,9 +702,9 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   }
 
   CUtensorMap tx, ty;
-  rc = cached_tmap(&tx, p.x, p.batch, p.height, p.width, p.x_ctot, 64, kTileW + 2, kHaloH);
+  rc = cached_tmap(&tx, p.x, p.batch, p.height, p.width, p.x_ctot, 64, kTileW + 2, kWgTileH + 2);
   if (rc != XMM_OK) return rc;
-  rc = cached_tmap(&ty, p.dy, p.batch, p.height, p.width, p.dy_ctot, 64, kTileW, kTileH);
+  rc = cached_tmap(&ty, p.dy, p.batch, p.height, p.width, p.dy_ctot, 64, kTileW, kWgTileH);
   if (rc != XMM_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
