@@ -75,8 +75,11 @@ struct DxCfg {
   // per-warp carry mailboxes: [parity][A = D_0 of column 15 | B = unfinished column 15][half-warp row][kWarpCols] fp32
   static constexpr int kWarpMailBytes = 2 * 2 * 2 * kWarpCols * 4;
   static constexpr int kMailBytes = kDxEpiWarps * kWarpMailBytes;
-  static size_t smem_bytes(uint32_t w_bytes, int stages) {
-    return 1024 + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kOutBytes + kMailBytes + kBarBytes;
+  // side-input tile (mask / residual of the output pixels): [8 rows][16 px] x NT bf16, TMA swizzled, double buffered
+  static constexpr int kSideTileBytes = kDxTileH * kDxTileW * NT * 2;
+  static size_t smem_bytes(uint32_t w_bytes, int stages, int nside = 0) {
+    return 1024 + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kOutBytes + kMailBytes +
+           size_t(2 * nside) * kSideTileBytes + kBarBytes + 4 * 8;
   }
 };
 
@@ -195,7 +198,7 @@ template <int KC, int NT>
 __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const ConvEpilogue& epi,
                                                  const CUtensorMap* tmap_out, uint32_t t_addr, uint64_t* tempty, int b,
                                                  int ty, int tx, int tiles_x, bool pre, bool has_pend, bool direct, int H,
-                                                 int W) {
+                                                 int W, const uint8_t* const* side_tiles = nullptr) {
   using Cfg = DxCfg<KC, NT>;
   const int y = ty * kDxTileH + w.prow;
   const int x = w.last_col ? tx * kDxTileW - 1 : tx * kDxTileW + w.pcol;
@@ -260,7 +263,15 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
     const int col = w.col_w + cc * 16;
     if (valid) {
       if (use_tma) {
-        conv_epilogue_math<NT, 16>(epi, nullptr, v, col, b, y, x, H, W);
+        StagedSides st;
+        const int ps = w.prow * kDxTileW + ((w.pcol + 1) & 15);  // this lane's pixel inside the CTA-wide side tile
+        st.base[0] = side_tiles ? side_tiles[0] : nullptr;
+        st.base[1] = side_tiles ? side_tiles[1] : nullptr;
+        st.base[2] = side_tiles ? side_tiles[2] : nullptr;
+        st.row_off = uint32_t(ps * NT * 2);
+        st.chunk0 = uint32_t(col / 8);
+        st.xor_mask = NT == 32 ? uint32_t((ps >> 1) & 3) : uint32_t(ps & 7);
+        conv_epilogue_math<NT, 16>(epi, nullptr, v, col, b, y, x, H, W, side_tiles ? &st : nullptr);
         const int p = (w.lane >> 4) * kDxTileW + ((w.pcol + 1) & 15);  // box pixel: lane 15 is the box's column 0
         *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2)) = pack8(v);
         *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2 + 1)) = pack8(v + 8);
@@ -290,10 +301,15 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
   w.par ^= 1;
 }
 
+// Tensor maps of the side inputs (mask, r1, r2) that are staged through shared memory (ConvArgs::side_mask).
+struct DxSideMaps {
+  CUtensorMap m[3];
+};
+
 template <int KC, int NT>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
-                  const ConvArgs args) {
+                  const __grid_constant__ DxSideMaps side_maps, const ConvArgs args) {
   using Cfg = DxCfg<KC, NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -302,13 +318,17 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   uint8_t* stage_s = smem + ((args.w_bytes + Cfg::kBiasBytes + 1023) & ~1023u);
   uint8_t* out_s = stage_s + size_t(args.stages) * Cfg::kStageBytes;  // per-warp staging tiles for the TMA stores
   uint8_t* mail_s = out_s + Cfg::kOutBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mail_s + Cfg::kMailBytes);
+  const int nside = __popc(args.side_mask);
+  uint8_t* side_s = mail_s + Cfg::kMailBytes;  // [2 buffers][nside] side-input tiles (1 KB aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_s + size_t(2 * nside) * Cfg::kSideTileBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 4;
   uint64_t* w_bar = tempty_bar + 4;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* sfull_bar = w_bar + 1;   // [2]
+  uint64_t* sempty_bar = sfull_bar + 2;  // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -332,6 +352,10 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       ptx::mbar_init(&tempty_bar[a], kDxEpiWarps);
     }
     ptx::mbar_init(w_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&sfull_bar[a], 1);
+      ptx::mbar_init(&sempty_bar[a], kDxEpiWarps);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
@@ -363,6 +387,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       }
       int stage = 0;
       uint32_t phase = 0;
+      int sbuf = 0;
+      uint32_t sphase = 0;
       for (int r0 = g0; r0 < t1; r0 += run_step) {
         DxTile t(r0, args.tiles_x, args.tiles_y);
         for (int g = r0; g < r0 + run_len; ++g, t.next(args.tiles_x, args.tiles_y)) {
@@ -377,6 +403,23 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             if (++stage == args.stages) {
               stage = 0;
               phase ^= 1u;
+            }
+          }
+          if (nside > 0 && g >= t0) {  // the output pixels' mask / residual tiles (not for pre-tiles)
+            ptx::mbar_wait(&sempty_bar[sbuf], sphase ^ 1u);
+            ptx::mbar_expect_tx(&sfull_bar[sbuf], uint32_t(nside) * Cfg::kSideTileBytes);
+            uint8_t* dst = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
+            const int coff[3] = {args.epi.mask_coff, args.epi.r1_coff, args.epi.r2_coff};
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              if (args.side_mask & (1 << k)) {
+                ptx::tma_load_4d(dst, &side_maps.m[k], &sfull_bar[sbuf], coff[k], t.tx * kDxTileW - 1, t.ty * kDxTileH,
+                                 t.b);
+                dst += Cfg::kSideTileBytes;
+              }
+            if (++sbuf == 2) {
+              sbuf = 0;
+              sphase ^= 1u;
             }
           }
         }
@@ -436,6 +479,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     const bool direct = args.epi.pixel_shuffle != 0;  // (inverse) pixel shuffle scatters: direct stores
     int acc = 0;
     uint32_t acc_phase = 0;
+    int sbuf = 0;
+    uint32_t sphase = 0;
     for (int r0 = g0; r0 < t1; r0 += run_step) {
       DxTile t(r0, args.tiles_x, args.tiles_y);  // advanced incrementally: no divisions in the tile loop
       for (int g = r0; g < r0 + run_len; ++g) {
@@ -445,8 +490,30 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         XMM_PROF_T0();
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(w.q * 32) << 16) + uint32_t(acc * Cfg::kAccCols);
+        const bool sides = nside > 0 && g >= t0;
+        const uint8_t* side_tiles[3] = {nullptr, nullptr, nullptr};
+        if (sides) {
+          ptx::mbar_wait(&sfull_bar[sbuf], sphase);
+          const uint8_t* src = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (args.side_mask & (1 << k)) {
+              // tile 0 of a strip stores (and reads its side inputs) directly: see dx_epilogue_tile
+              side_tiles[k] = src;
+              src += Cfg::kSideTileBytes;
+            }
+        }
         dx_epilogue_tile<KC, NT>(w, args.epi, &tmap_out, t_addr, &tempty_bar[acc], t.b, t.ty, t.tx, args.tiles_x,
-                                 /*pre=*/g < t0, /*has_pend=*/(t.tx > 0) && (g != r0), direct, args.height, args.width);
+                                 /*pre=*/g < t0, /*has_pend=*/(t.tx > 0) && (g != r0), direct, args.height, args.width,
+                                 sides ? side_tiles : nullptr);
+        if (sides) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&sempty_bar[sbuf]);
+          if (++sbuf == 2) {
+            sbuf = 0;
+            sphase ^= 1u;
+          }
+        }
         XMM_PROF_ADD(5);
         if (++acc == Cfg::kAccStages) {
           acc = 0;

@@ -80,6 +80,7 @@ struct ConvArgs {
   int tiles_x, tiles_y, num_tiles;
   int stages;
   int strip_rr;  // conv3x3_dx: 1 = whole strips dealt round-robin to the CTAs, 0 = equal contiguous tile ranges
+  int side_mask; // conv3x3_dx: bit k set = side input k (0 mask, 1 r1, 2 r2) is staged through shared memory by TMA
   ConvEpilogue epi;
 #ifdef XMM_CONV_PROFILE
   long long* prof;  // [gridDim.x][8] cycle counters (tools/probe.cu only)
@@ -135,9 +136,23 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 // Fused epilogue arithmetic for NC accumulator columns [col0, col0+NC) of one pixel, in place on v (raw fp32 sums):
 // bias (bias_s == nullptr: already added), LeakyReLU, LeakyReLU' mask, scale, residuals.
+// Side inputs (mask, r1, r2) are read from global memory, or -- when `staged` is given -- from shared-memory copies
+// a TMA load placed there: staged[k] points at this lane's NC channels of side input k (nullptr: not staged), with
+// consecutive 16-byte chunks at staged_xor-swizzled positions (see conv3x3_dx.cuh).
+struct StagedSides {
+  const uint8_t* base[3];  // tile base per side input (mask, r1, r2) or nullptr
+  uint32_t row_off;        // byte offset of this lane's pixel row inside the tile
+  uint32_t chunk0;         // first 16-byte chunk index of this lane's channels
+  uint32_t xor_mask;       // swizzle: chunk ^= xor_mask
+};
+__device__ __forceinline__ uint4 staged_chunk(const StagedSides& s, int k, int q) {
+  return *reinterpret_cast<const uint4*>(s.base[k] + s.row_off + (((s.chunk0 + uint32_t(q)) ^ s.xor_mask) << 4));
+}
+
 template <int NT, int NC>
 __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const float* __restrict__ bias_s,
-                                                   float (&v)[NC], int col0, int b, int y, int x, int H, int W) {
+                                                   float (&v)[NC], int col0, int b, int y, int x, int H, int W,
+                                                   const StagedSides* staged = nullptr) {
   static_assert(NC % 8 == 0, "whole 16-byte accesses");
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
@@ -150,7 +165,7 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
       float m[8];
-      unpack8(__ldg(mp + q), m);
+      unpack8((staged != nullptr && staged->base[0] != nullptr) ? staged_chunk(*staged, 0, q) : __ldg(mp + q), m);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[q * 8 + i] *= (m[i] > 0.f ? 1.f : e.mask_slope);
     }
@@ -164,7 +179,7 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
       float m[8];
-      unpack8(__ldg(rp + q), m);
+      unpack8((staged != nullptr && staged->base[1] != nullptr) ? staged_chunk(*staged, 1, q) : __ldg(rp + q), m);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[q * 8 + i] = fmaf(e.s1, m[i], v[q * 8 + i]);
     }
@@ -174,7 +189,7 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
       float m[8];
-      unpack8(__ldg(rp + q), m);
+      unpack8((staged != nullptr && staged->base[2] != nullptr) ? staged_chunk(*staged, 2, q) : __ldg(rp + q), m);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[q * 8 + i] = fmaf(e.s2, m[i], v[q * 8 + i]);
     }

@@ -149,7 +149,21 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   a.tiles_x = (p.width + kDxTileW - 1) / kDxTileW;
   a.tiles_y = (p.height + kDxTileH - 1) / kDxTileH;
   a.num_tiles = a.tiles_x * a.tiles_y * p.batch;
-  const size_t fixed = Cfg::smem_bytes(a.w_bytes, 0);
+  // side inputs (LeakyReLU' mask, residuals) travel through shared memory by TMA unless the output is pixel-shuffled
+  // (XMM_DX_SIDES=0 keeps the per-lane global loads, for experiments)
+  static const int sides_env = [] { const char* e = getenv("XMM_DX_SIDES"); return e ? atoi(e) : 1; }();
+  const void* side_ptr[3] = {p.mask, p.r1, p.r2};
+  const int side_ctot[3] = {p.mask_ctot, p.r1_ctot, p.r2_ctot};
+  int nside = 0;
+  if (p.pixel_shuffle == 0 && sides_env)
+    for (int k = 0; k < 3; ++k)
+      if (side_ptr[k] != nullptr) { a.side_mask |= 1 << k; ++nside; }
+  size_t fixed = Cfg::smem_bytes(a.w_bytes, 0, nside);
+  if (nside > 0 && fixed + 4 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin)) {  // keep >= 4 pipeline stages
+    a.side_mask = 0;
+    nside = 0;
+    fixed = Cfg::smem_bytes(a.w_bytes, 0, 0);
+  }
   if (fixed + 2 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin))
     return fail(XMM_ERR_UNSUPPORTED_SHAPE,
                 "conv3x3: weights of cin=%d cout=%d (%u B) do not fit in shared memory next to 2 pipeline stages",
@@ -157,7 +171,7 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   int stages = int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes);
   if (stages > kMaxStages) stages = kMaxStages;
   a.stages = stages;
-  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages);
+  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages, nside);
   fill_epilogue(a.epi, p);
   CUtensorMap tmap;
   int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, kDxTileW, kDxPatchH);
@@ -166,6 +180,14 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   if (p.pixel_shuffle == 0) {
     rc = cached_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, Cfg::kWarpCols, kDxTileW, 2);
     if (rc != XMM_OK) return rc;
+  }
+  DxSideMaps sides;
+  for (int k = 0; k < 3; ++k) {
+    sides.m[k] = tmap;
+    if (a.side_mask & (1 << k)) {
+      rc = cached_tmap(&sides.m[k], side_ptr[k], p.batch, p.height, p.width, side_ctot[k], NT, kDxTileW, kDxTileH);
+      if (rc != XMM_OK) return rc;
+    }
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -179,7 +201,7 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   const long long nstrips = (long long)a.tiles_y * p.batch;
   // (cin <= 64 is not DRAM-bound: there the round-robin's wave quantisation only pays off with many strips)
   a.strip_rr = rr_env >= 0 ? (rr_env != 0) : (nstrips >= 4LL * grid && (a.nchunks >= 3 || nstrips >= 16LL * grid));
-  conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, a);
+  conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, sides, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
