@@ -55,6 +55,8 @@ typedef struct {
   float scale;
   int n_off, n_count;  /* rows [n_off, n_off+n_count) of the packed layer; the segment's own row
                           index is n - n_off                                                    */
+  int part;            /* 0: bf16(w); 1: bf16(w - bf16(w)), the low-order half of a split-precision
+                          layer (conv_last on the tensor cores keeps fp32-accurate weights)      */
 } xmm_pack_segment;
 
 typedef struct {
@@ -199,6 +201,9 @@ typedef struct {
   float* pre;          /* optional un-clamped copy (training)                              */
   int batch, cout, height, width, filters;  /* cout 1..4                                    */
   int clamp;
+  const void* wblob;  /* optional: packed split-precision layer (nt = 32, kc = 32, rows [0,cout) = bf16(w),
+                         rows [16,16+cout) = low-order halves, bias in the blob) -> tensor-core path;
+                         NULL -> CUDA-core path reading `weight` / `bias`                           */
 } xmm_conv_last_params;
 int xmm_conv_last(const xmm_conv_last_params* p, void* stream);
 

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libxmm_b200.so")
 
 class PackSegment(Structure):
     _fields_ = [("src", c_void_p), ("src_cin", c_int), ("o_off", c_int), ("i_off", c_int), ("transpose", c_int),
-                ("k_off", c_int), ("k_count", c_int), ("scale", c_float), ("n_off", c_int), ("n_count", c_int)]
+                ("k_off", c_int), ("k_count", c_int), ("scale", c_float), ("n_off", c_int), ("n_count", c_int),
+                ("part", c_int)]
 
 
 class PackJob(Structure):
@@ -58,7 +59,7 @@ class ConvLastParams(Structure):
                 ("weight", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
                 ("out", c_void_p), ("pre", c_void_p),
                 ("batch", c_int), ("cout", c_int), ("height", c_int), ("width", c_int), ("filters", c_int),
-                ("clamp", c_int)]
+                ("clamp", c_int), ("wblob", c_void_p)]
 
 
 class WgradRole(Structure):

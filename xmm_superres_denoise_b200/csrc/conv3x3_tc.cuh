@@ -69,6 +69,13 @@ struct ConvEpilogue {
   // 1: PixelShuffle(2) store: out is [B][2H][2W][out_ctot]; column group g=(i,j) -> pixel (2y+i,2x+j)
   // 2: inverse (backward of 1): out is [B][H/2][W/2][out_ctot]; pixel (y,x) -> (y/2,x/2), channel block g=(y&1,x&1)
   int pixel_shuffle;
+  // Image mode (conv_last, generator_rrdb.py:48-54,107-108,132-135, on the tensor cores): img_out != nullptr.
+  // The packed layer holds bf16(w) in rows [0, img_cout) and the low-order halves bf16(w - bf16(w)) in rows
+  // [16, 16 + img_cout); out[b][o][y][x] = clamp?(acc[o] + acc[16+o] + bias[o] + img_res[...]) in fp32 NCHW.
+  float* img_out;
+  const float* img_res;
+  float* img_pre;   // optional copy of the un-clamped value (backward clamp gate)
+  int img_cout, img_clamp;
 };
 
 struct ConvArgs {
@@ -408,7 +415,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
 #ifdef XMM_EXP_NOEPI
         if (__uint_as_float(accr[0]) == 123.456f)
 #endif
-        if (valid) conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
+        if (valid) {
+          if (NT == 32 && args.epi.img_out != nullptr) {
+            const size_t hw = size_t(args.height) * args.width;
+            const size_t o0 = size_t(b) * args.epi.img_cout * hw + size_t(y) * args.width + x;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o < args.epi.img_cout) {
+                float v = __uint_as_float(accr[o]) + __uint_as_float(accr[16 + o]) + bias_s[o];
+                if (args.epi.img_res != nullptr) v += args.epi.img_res[o0 + o * hw];
+                if (args.epi.img_pre != nullptr) args.epi.img_pre[o0 + o * hw] = v;
+                args.epi.img_out[o0 + o * hw] = args.epi.img_clamp ? fminf(fmaxf(v, 0.0f), 1.0f) : v;
+              }
+            }
+          } else {
+            conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
+          }
+        }
       }
       XMM_PROF_ADD(5);
       acc ^= 1;

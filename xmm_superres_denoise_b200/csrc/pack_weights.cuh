@@ -44,6 +44,7 @@ __global__ void pack_jobs_kernel(const xmm_pack_job* __restrict__ jobs) {
               t = (2 - dy) * 3 + (2 - dx);
             }
             val = sg.scale * sg.src[(size_t(o) * sg.src_cin + i) * 9 + t];
+            if (sg.part == 1) val -= __bfloat162float(__float2bfloat16_rn(val));  // low-order half
           }
         }
       }

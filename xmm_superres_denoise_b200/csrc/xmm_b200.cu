@@ -90,10 +90,18 @@ void fill_epilogue(ConvEpilogue& e, const xmm_conv3x3_params& p) {
   e.r2 = static_cast<const __nv_bfloat16*>(p.r2); e.r2_ctot = p.r2_ctot; e.r2_coff = p.r2_coff;
   e.out = static_cast<__nv_bfloat16*>(p.out); e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
   e.pixel_shuffle = p.pixel_shuffle;
+  e.img_out = nullptr; e.img_res = nullptr; e.img_pre = nullptr; e.img_cout = 0; e.img_clamp = 0;
 }
 
+struct ImageOut {
+  float* out;
+  const float* res;
+  float* pre;
+  int cout, clamp;
+};
+
 template <int KC, int NT, int MODE>
-int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
+int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream, const ImageOut* img = nullptr) {
   using Cfg = ConvCfg<KC, NT, MODE>;
   ConvArgs a{};
   a.wblob = p.wblob;
@@ -117,6 +125,10 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
   const size_t smem = Cfg::smem_bytes(a.w_bytes, stages);
 
   fill_epilogue(a.epi, p);
+  if (img != nullptr) {
+    a.epi.img_out = img->out; a.epi.img_res = img->res; a.epi.img_pre = img->pre;
+    a.epi.img_cout = img->cout; a.epi.img_clamp = img->clamp;
+  }
 
   CUtensorMap tmap;
   int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, Cfg::kPitchPx, kHaloH);
@@ -625,6 +637,19 @@ extern "C" int xmm_conv_last(const xmm_conv_last_params* pp, void* stream) {
   XMM_REQUIRE(p.batch > 0 && p.height > 0 && p.width > 0, "conv_last: bad shape");
   XMM_REQUIRE(p.in_ctot % 8 == 0 && p.in_coff % 8 == 0 && p.in_coff + p.filters <= p.in_ctot,
               "conv_last: input channel window");
+  if (p.wblob != nullptr) {  // tensor-core path: an F -> 32-row split-precision layer with the image epilogue
+    XMM_REQUIRE(p.filters % 32 == 0 && p.in_ctot % 8 == 0 && p.in_coff % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.wblob) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0,
+                "conv_last: tensor-core path needs filters %% 32 == 0 and 16-byte aligned buffers");
+    xmm_conv3x3_params c{};
+    c.in = p.in; c.in_ctot = p.in_ctot; c.in_coff = p.in_coff; c.cin = p.filters;
+    c.wblob = p.wblob; c.kc = 32; c.cout = 32;
+    c.batch = p.batch; c.height = p.height; c.width = p.width;
+    c.lrelu_slope = 1.0f; c.s0 = 1.0f;
+    c.out = p.out; c.out_ctot = 32; c.out_coff = 0;  // unused in image mode
+    ImageOut img{p.out, p.residual, p.pre, p.cout, p.clamp};
+    return launch_conv<32, 32, kTapHalo>(c, dev, static_cast<cudaStream_t>(stream), &img);
+  }
   ConvLastArgs a{};
   a.in = static_cast<const __nv_bfloat16*>(p.in); a.in_ctot = p.in_ctot; a.in_coff = p.in_coff;
   a.w = p.weight; a.bias = p.bias; a.residual = p.residual; a.out = p.out; a.pre = p.pre;

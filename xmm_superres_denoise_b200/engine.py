@@ -40,6 +40,7 @@ class _Segment:
     scale: float
     n_off: int = 0
     n_count: int = -1  # -1: all rows of the blob
+    part: int = 0      # 1: low-order half bf16(w - bf16(w)) of a split-precision layer
 
 
 @dataclass
@@ -117,6 +118,7 @@ class WeightArena:
                     s_c.src, s_c.src_cin, s_c.o_off, s_c.i_off = s.param.data_ptr(), s.src_cin, s.o_off, s.i_off
                     s_c.transpose, s_c.k_off, s_c.k_count, s_c.scale = s.transpose, s.k_off, s.k_count, s.scale
                     s_c.n_off, s_c.n_count = s.n_off, (b.nt if s.n_count < 0 else s.n_count)
+                    s_c.part = s.part
             raw = bytes(jobs)
             self._jobs_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
             self._key = key
@@ -205,6 +207,19 @@ class RRDBEngine(_LayerPlans):
             for s in range(self.num_upsample):
                 self._add_forward_layer(f"f.up{s}", g.upsampling[3 * s], perm=1)
             self._add_forward_layer("f.hr", g.HRconv)
+        # conv_last (F -> out_channels) on the tensor cores with fp32-accurate weights: a 32-row layer whose rows
+        # [0, cout) hold bf16(w) and rows [16, 16 + cout) the low-order halves bf16(w - bf16(w)); the image epilogue
+        # of the conv kernel adds the two partial sums, the bias and the DN residual and clamps (fp32 NCHW out)
+        cl = g.conv_last
+        co = cl.weight.shape[0]
+        if co <= 4 and self.nf % 32 == 0:
+            self.arena.add(_Blob("f.last", 32, 32, self.nf // 32,
+                                 [_Segment(cl.weight, self.nf, 0, 0, 0, 0, self.nf, 1.0, 0, co, 0),
+                                  _Segment(cl.weight, self.nf, 0, 0, 0, 0, self.nf, 1.0, 16, co, 1)],
+                                 cl.bias, 0, bias_n=co))
+            self._last_blob = "f.last"
+        else:
+            self._last_blob = None
         self._bufs: Dict[tuple, Dict[str, torch.Tensor]] = {}
         # how a dense block's five dependent convs are launched (ops.CHAIN_*): layer by layer is the measured
         # optimum today; XMM_CHAIN_MODE=1 selects the pipelined single-launch kernel (F=32 only)
@@ -213,6 +228,9 @@ class RRDBEngine(_LayerPlans):
     @property
     def gen(self) -> nn.Module:
         return self._gen_ref[0]
+
+    def _last_ptr(self):
+        return self.arena.ptr(self._last_blob) if self._last_blob is not None else None
 
     # ------------------------------------------------------------------ buffers
     def _inference_buffers(self, b: int, h: int, w: int, device: torch.device) -> Dict[str, torch.Tensor]:
@@ -302,7 +320,8 @@ class RRDBEngine(_LayerPlans):
             if g.in_channels != g.out_channels:
                 raise RuntimeError("GeneratorRRDB_DN adds its input to its output: in_channels must equal out_channels")
             out = torch.empty(b, g.out_channels, h, w, dtype=torch.float32, device=x.device)
-            ops.conv_last(bufs["trunk"], 0, g.conv_last.weight, g.conv_last.bias, out, residual=x, clamp=True)
+            ops.conv_last(bufs["trunk"], 0, g.conv_last.weight, g.conv_last.bias, out, residual=x, clamp=True,
+                          wblob_ptr=self._last_ptr())
             return out
         cur = bufs["trunk"]
         for s in range(self.num_upsample):
@@ -311,7 +330,7 @@ class RRDBEngine(_LayerPlans):
         self._run(self._conv("f.hr", cur, 0, self.nf, bufs["hr"], 0, lrelu=0.2))
         hh, ww = cur.shape[1], cur.shape[2]
         out = torch.empty(b, g.out_channels, hh, ww, dtype=torch.float32, device=x.device)
-        ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, clamp=True)
+        ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, clamp=True, wblob_ptr=self._last_ptr())
         return out
 
 

@@ -102,7 +102,8 @@ class TrainEngine(RRDBEngine):
             if g.in_channels != g.out_channels:
                 raise RuntimeError("GeneratorRRDB_DN adds its input to its output: in_channels must equal out_channels")
             out = torch.empty(b, g.out_channels, h, w, dtype=torch.float32, device=x.device)
-            ops.conv_last(bufs["trunk"], 0, g.conv_last.weight, g.conv_last.bias, out, residual=x, pre=bufs["pre"])
+            ops.conv_last(bufs["trunk"], 0, g.conv_last.weight, g.conv_last.bias, out, residual=x, pre=bufs["pre"],
+                          wblob_ptr=self._last_ptr())
             return out, bufs
         cur = bufs["trunk"]
         for s in range(self.num_upsample):
@@ -110,7 +111,7 @@ class TrainEngine(RRDBEngine):
             cur = bufs[f"up{s}"]
         self._run(self._conv("f.hr", cur, 0, self.nf, bufs["hr"], 0, lrelu=0.2))
         out = torch.empty(b, g.out_channels, cur.shape[1], cur.shape[2], dtype=torch.float32, device=x.device)
-        ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, pre=bufs["pre"])
+        ops.conv_last(bufs["hr"], 0, g.conv_last.weight, g.conv_last.bias, out, pre=bufs["pre"], wblob_ptr=self._last_ptr())
         return out, bufs
 
     # ------------------------------------------------------------------ backward

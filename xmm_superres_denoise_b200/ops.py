@@ -135,8 +135,9 @@ def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 
 def conv_last(inp: torch.Tensor, in_coff: int, weight: torch.Tensor, bias: Optional[torch.Tensor],
               out: torch.Tensor, residual: Optional[torch.Tensor] = None, pre: Optional[torch.Tensor] = None,
-              clamp: bool = True) -> None:
-    """bf16 NHWC features -> fp32 NCHW image (+ residual, clamp) (generator_rrdb.py:48-54,107-108,132-135)."""
+              clamp: bool = True, wblob_ptr: Optional[int] = None) -> None:
+    """bf16 NHWC features -> fp32 NCHW image (+ residual, clamp) (generator_rrdb.py:48-54,107-108,132-135).
+    wblob_ptr: packed split-precision layer -> tensor-core path (see xmm_conv_last_params.wblob)."""
     _nhwc(inp, "conv_last input")
     _lib.require_cuda_tensor(weight, torch.float32, "conv_last weight")
     _lib.require_cuda_tensor(out, torch.float32, "conv_last output")
@@ -155,6 +156,7 @@ def conv_last(inp: torch.Tensor, in_coff: int, weight: torch.Tensor, bias: Optio
     p.out = out.data_ptr()
     p.batch, p.cout, p.height, p.width, p.filters = b, weight.shape[0], h, w, weight.shape[1]
     p.clamp = 1 if clamp else 0
+    p.wblob = wblob_ptr
     _lib.check(_lib.load().xmm_conv_last(ctypes.byref(p), _lib.stream_ptr()))
     _count()
 
