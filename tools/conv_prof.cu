@@ -69,7 +69,7 @@ static void run(int B, int H, int W, int k, int stages_cap) {
     CK(cudaMemset(prof, 0, 148 * 12 * sizeof(long long)));
     cudaEventRecord(e0);
     if constexpr (DX) { DxSideMaps sm_; sm_.m[0] = sm_.m[1] = sm_.m[2] = tmap; conv3x3_dx_kernel<KC, NT><<<148, kDxThreads, Cfg::smem_bytes(a.w_bytes, stages)>>>(tmap, tmap_o, sm_, a); }
-    if constexpr (!DX) conv3x3_tc_kernel<KC, NT, 0><<<148, kConvThreads, Cfg::smem_bytes(a.w_bytes, stages)>>>(tmap, a);
+    if constexpr (!DX) conv3x3_tc_kernel<KC, NT, 0><<<148, kConvThreads, Cfg::smem_bytes(a.w_bytes, stages)>>>(tmap, tmap, a);
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1);

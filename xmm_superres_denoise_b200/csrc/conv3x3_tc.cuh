@@ -87,6 +87,7 @@ struct ConvArgs {
   int tiles_x, tiles_y, num_tiles;
   int stages;
   int strip_rr;  // conv3x3_dx: 1 = whole strips dealt round-robin to the CTAs, 0 = equal contiguous tile ranges
+  int tma_store; // conv3x3_tc: 1 = epilogue warps stage their [4 rows][8 px] x NT result and TMA-store it
   int side_mask; // conv3x3_dx: bit k set = side input k (0 mask, 1 r1, 2 r2) is staged through shared memory by TMA
   ConvEpilogue epi;
 #ifdef XMM_CONV_PROFILE
@@ -113,8 +114,11 @@ struct ConvCfg {
   static constexpr int kBiasBytes = NT * 4;
   // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] wbar + tmem ptr
   static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 16;
+  // per-warp output staging for the TMA store ([4 rows][8 px] x NT bf16, swizzled; 4 warps, double buffered)
+  static constexpr int kWarpOutBytes = (NT <= 64) ? 32 * NT * 2 : 0;
+  static constexpr int kOutBytes = 4 * 2 * kWarpOutBytes;
   static size_t smem_bytes(uint32_t w_bytes, int stages) {
-    return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kBarBytes;
+    return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kOutBytes + kBarBytes;
   }
 };
 
@@ -242,14 +246,16 @@ __device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const fl
 
 template <int KC, int NT, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs args) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                  const ConvArgs args) {
   using Cfg = ConvCfg<KC, NT, MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;                                                   // weights image
   float* bias_s = reinterpret_cast<float*>(smem + args.w_bytes);         // NT floats (same bulk copy)
   uint8_t* stage_s = smem + ((args.w_bytes + Cfg::kBiasBytes + 1023) & ~1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + size_t(args.stages) * Cfg::kStageBytes);
+  uint8_t* out_s = stage_s + size_t(args.stages) * Cfg::kStageBytes;  // 1 KB aligned (stage sizes are)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_s + Cfg::kOutBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
@@ -387,6 +393,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
     const int m = q * 32 + lane;
     const int py = m >> 3, px = m & 7;
     ptx::mbar_wait(w_bar, 0);  // bias rides with the weights
+    // TMA-store path: this warp's [4 rows][8 px] x NT result goes through its own swizzled staging tile (rows of
+    // NT*2 = 64 B: SWIZZLE_64B, 128 B: SWIZZLE_128B) -- per-lane 16-byte global stores at a 64..640-byte pitch cost
+    // ~512 L1 transactions per tile on the datapath the MMA operand reads share.
+    const bool use_tma = Cfg::kOutBytes > 0 && args.tma_store != 0;
+    uint8_t* my_out = out_s + (warp - 2) * 2 * Cfg::kWarpOutBytes;
+    const uint32_t sw_xor = NT == 32 ? uint32_t((lane >> 1) & 3) : uint32_t(lane & 7);
+    int obuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
@@ -402,6 +415,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
       XMM_PROF_T0();
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * NT);
+      uint8_t* stage = my_out + obuf * Cfg::kWarpOutBytes;
+      if (use_tma) {  // the store issued two tiles ago has finished reading this staging tile
+        if (ptx::elect_one()) ptx::bulk_wait_read<1>();
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int cc = 0; cc < NT / 32; ++cc) {
         uint32_t accr[32];
@@ -428,15 +446,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvArgs ar
                 args.epi.img_out[o0 + o * hw] = args.epi.img_clamp ? fminf(fmaxf(v, 0.0f), 1.0f) : v;
               }
             }
+          } else if (use_tma) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]);
+            conv_epilogue_math<NT, 32>(args.epi, bias_s, v, cc * 32, b, y, x, args.height, args.width);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(stage + lane * (NT * 2) + (((uint32_t(cc * 4 + j)) ^ sw_xor) << 4)) = pack8(v + j * 8);
           } else {
             conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
           }
         }
       }
+      if (use_tma) {
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (ptx::elect_one()) {
+          ptx::tma_store_4d(&tmap_out, stage, args.epi.out_coff, tx * kTileW, ty * kTileH + 4 * q, b);
+          ptx::bulk_commit();
+        }
+        obuf ^= 1;
+      }
       XMM_PROF_ADD(5);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (use_tma && ptx::elect_one()) ptx::bulk_wait<0>();  // stores complete before the CTA (and its smem) goes away
     if (warp == 2 && lane == 0) { XMM_PROF_FLUSH(4); XMM_PROF_FLUSH(5); }
   }
 

@@ -133,6 +133,14 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
   CUtensorMap tmap;
   int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, Cfg::kPitchPx, kHaloH);
   if (rc != XMM_OK) return rc;
+  // plain NHWC outputs of narrow layers leave through per-warp TMA stores (XMM_TC_TMA_STORE=0: direct stores)
+  static const int tma_env = [] { const char* e = getenv("XMM_TC_TMA_STORE"); return e ? atoi(e) : 1; }();
+  CUtensorMap tmap_out = tmap;
+  a.tma_store = (Cfg::kOutBytes > 0 && p.pixel_shuffle == 0 && img == nullptr && tma_env) ? 1 : 0;
+  if (a.tma_store) {
+    rc = cached_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, NT, kTileW, 4);
+    if (rc != XMM_OK) return rc;
+  }
 
   static bool attr_set = false;  // per instantiation; benign race (idempotent call)
   if (!attr_set) {
@@ -141,7 +149,7 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
     attr_set = true;
   }
   const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
-  conv3x3_tc_kernel<KC, NT, MODE><<<grid, kConvThreads, smem, stream>>>(tmap, a);
+  conv3x3_tc_kernel<KC, NT, MODE><<<grid, kConvThreads, smem, stream>>>(tmap, tmap_out, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
