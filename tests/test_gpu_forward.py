@@ -307,3 +307,30 @@ def test_generator_64_filters_matches_oracle(dev, kind):
     # split-layer arithmetic itself is held to 2.4e-3 by test_standalone_rrdb_block[64].  Recorded in DESIGN.md.
     assert r < (REL_L2_BF16 if kind == "dn" else 1.5 * REL_L2_BF16)
     assert psnr_db(got, want) > 80.0
+
+
+def test_small_batch_inference_uses_cuda_graph_and_matches_eager(dev):
+    """Batches <= 8 replay a captured launch sequence: same result as the eager launches, also after the weights
+    change (re-pack happens outside the graph) and when shapes alternate (buffers / graphs are dropped together)."""
+    sd = O.init_state_dict("dn", 1, 1, 32, 1, 1, seed=3)
+    m = _model("dn", 32, 1, sd, dev)
+    x1 = torch.rand(2, 1, 56, 72, generator=torch.Generator().manual_seed(0)).to(dev)
+    x2 = torch.rand(1, 1, 40, 48, generator=torch.Generator().manual_seed(1)).to(dev)
+    with torch.no_grad():
+        eng = m._get_engine()
+        eng.use_graph = False
+        e1, e2 = m(x1).clone(), m(x2).clone()
+        eng.use_graph = True
+        for _ in range(2):  # capture, then replay; alternate shapes
+            g1 = m(x1)
+            g2 = m(x2)
+            assert torch.equal(g1, e1) and torch.equal(g2, e2)
+        assert len(eng._graphs) >= 1
+        # weights change -> re-pack outside the graph, replay must see the new weights
+        for p in m.parameters():
+            p.mul_(0.5)
+        eng.use_graph = False
+        e3 = m(x1).clone()
+        eng.use_graph = True
+        assert torch.equal(m(x1), e3)
+        assert not torch.equal(e3, e1)

@@ -224,6 +224,10 @@ class RRDBEngine(_LayerPlans):
         # how a dense block's five dependent convs are launched (ops.CHAIN_*): layer by layer is the measured
         # optimum today; XMM_CHAIN_MODE=1 selects the pipelined single-launch kernel (F=32 only)
         self.chain_mode = int(os.environ.get("XMM_CHAIN_MODE", ops.CHAIN_LAYER_BY_LAYER))
+        # CUDA-graph replay of small-batch inference (XMM_CUDA_GRAPH=0 disables)
+        self.use_graph = os.environ.get("XMM_CUDA_GRAPH", "1") != "0"
+        self.graph_max_batch = 8
+        self._graphs: Dict[tuple, tuple] = {}
 
     @property
     def gen(self) -> nn.Module:
@@ -238,6 +242,7 @@ class RRDBEngine(_LayerPlans):
         bufs = self._bufs.get(key)
         if bufs is None:
             self._bufs.clear()  # one live shape at a time: these are multi-GB at batch 64
+            self._graphs.clear()  # captured launch sequences point into the dropped buffers
             f = self.nf
             bufs = {f"rdb{r}": torch.empty(b, h, w, 5 * f, dtype=torch.bfloat16, device=device) for r in range(3)}
             bufs["fea"] = torch.empty(b, h, w, f, dtype=torch.bfloat16, device=device)
@@ -309,11 +314,38 @@ class RRDBEngine(_LayerPlans):
 
     @torch.no_grad()
     def forward_inference(self, x: torch.Tensor) -> torch.Tensor:
+        """Inference forward.  Small batches (<= ``graph_max_batch`` images) are launch-bound -- ~80-150 kernel
+        launches of ~10 us each through Python -- so their launch sequence is captured once per input shape into a
+        CUDA graph and replayed (weights are re-packed outside the graph; a moved parameter storage re-captures)."""
         self._check_input(x)
-        g = self.gen
         x = x.contiguous().float()
-        b, _, h, w = x.shape
         self.arena.ensure(x.device)
+        if not (self.use_graph and x.shape[0] <= self.graph_max_batch) or torch.cuda.is_current_stream_capturing():
+            return self._forward_inference_eager(x)
+        key = (tuple(x.shape), str(x.device), self.arena._key)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            static_in = x.clone()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):  # first-call setup (function attributes, TMA descriptors) outside the capture
+                self._forward_inference_eager(static_in)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_inference_eager(static_in)
+            entry = (graph, static_in, static_out)
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
+
+    def _forward_inference_eager(self, x: torch.Tensor) -> torch.Tensor:
+        g = self.gen
+        b, _, h, w = x.shape
         bufs = self._inference_buffers(b, h, w, x.device)
         self._trunk_forward(x, [bufs["rdb0"], bufs["rdb1"], bufs["rdb2"]], bufs["fea"], bufs["trunk"])
         if self.kind == "dn":

@@ -68,6 +68,7 @@ class TrainEngine(RRDBEngine):
         bufs = self._bufs.get(key)
         if bufs is None:
             self._bufs.clear()
+            self._graphs.clear()
             f = self.nf
             bf = dict(dtype=torch.bfloat16, device=device)
             nrdb = 3 * self.nb
