@@ -399,22 +399,34 @@ def main() -> None:
         n_k = sum(n for _, _, _, n in prof_events)
 
         # ------------------------------------------------------------ end to end (host buffers)
-        def e2e_step():
-            c = counts_host.to(dev, non_blocking=True)
-            x = norm.normalize_counts(c, norm.lr_max, exposure=t_lr)
-            y = model(x)
-            out_host.copy_(y, non_blocking=True)
+        # the package's public host-to-host call: xmm_superres_denoise_b200.pipeline.InferencePipeline -- pinned int32
+        # counts in, fused prepare kernel + generator, pinned fp32 prediction out; H2D / compute / D2H on three
+        # streams, double buffered.  Every step copies its own input and reads back its own result.
+        from xmm_superres_denoise_b200.pipeline import InferencePipeline
 
-        for _ in range(2):
-            e2e_step()
+        pipe = InferencePipeline(model, norm, B, 416, 416, 416, exposure=t_lr)
+        counts_hosts = [counts_host.reshape(B, 416, 416), counts_host.reshape(B, 416, 416).clone().pin_memory()]
+        out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
+
+        def e2e_step(i):
+            s = i & 1
+            if i >= 2:
+                pipe.wait(s)  # the host output buffer of this slot is about to be overwritten
+            pipe.submit(counts_hosts[s], out_hosts[s])
+
+        for i in range(2):
+            e2e_step(i)
+        pipe.synchronize()
         barrier()
         s2, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s2.record()
-        for _ in range(args.steps):
-            e2e_step()
+        t_wall = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i + 2)
+        pipe.synchronize()
         t2.record()
         barrier()
-        e2e_ms = s2.elapsed_time(t2)
+        e2e_ms = max(s2.elapsed_time(t2), (time.perf_counter() - t_wall) * 1e3)  # device events vs host wall: the larger
 
     train_extra = {}
     if not args.no_train_extra:

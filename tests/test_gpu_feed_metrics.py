@@ -233,3 +233,31 @@ def test_model_wrapper_train_and_validation_steps(dev):
     for k in ("val/loss", "val/linear/psnr", "val/linear/ms_ssim", "val/linear/in/l1"):
         assert k in m.logged and torch.isfinite(torch.as_tensor(m.logged[k])), k
     assert m.in_metrics is None  # logged once (model.py:136-139)
+
+
+def test_inference_pipeline_overlapped_matches_serial(dev):
+    """pipeline.InferencePipeline (H2D / compute / D2H on three streams, double buffered) returns, for every
+    submitted batch, exactly what the serial prepare + generator + copy gives."""
+    from xmm_superres_denoise_b200.data import load_and_combine_simulations
+    from xmm_superres_denoise_b200.models import GeneratorRRDB_SR
+    from xmm_superres_denoise_b200.pipeline import InferencePipeline
+    from xmm_superres_denoise_b200.transforms import Normalize
+
+    torch.manual_seed(0)
+    model = GeneratorRRDB_SR(1, 1, 32, 1, num_upsample=1).to(dev).eval()
+    norm = Normalize(LR_MAX, HR_MAX, "sqrt")
+    mask = detector_mask(1)
+    rng = np.random.default_rng(3)
+    batches = [torch.from_numpy(rng.poisson(1.0, size=(2, 411, 403)).astype(np.int32)).pin_memory() for _ in range(5)]
+    outs = [torch.empty(2, 1, 832, 832).pin_memory() for _ in range(5)]
+    pipe = InferencePipeline(model, norm, 2, 411, 403, 416, det_mask=mask, exposure=20000.0)
+    for c, o in zip(batches, outs):
+        pipe.submit(c, o)
+    pipe.synchronize()
+    torch.cuda.synchronize()
+    mdev = torch.from_numpy(mask).to(dev)
+    for c, o in zip(batches, outs):
+        with torch.no_grad():
+            x = load_and_combine_simulations(416, c.to(dev), det_mask=mdev, normalizer=norm, which="lr", exposure=20000.0)
+            want = torch.clamp(model(x), 0, 1).cpu()
+        assert torch.equal(o, want)
