@@ -993,8 +993,10 @@ extern "C" int xmm_msssim_finalize(const xmm_msssim_finalize_params* pp, void* s
   a.nscales = p.nscales; a.batch = p.batch; a.channels = p.channels; a.k1 = p.k1; a.k2 = p.k2;
   a.st = reinterpret_cast<ScaleStats*>(p.stats_dev);
   a.value = p.value; a.img_val = p.img_val; a.kimg = p.kimg; a.gl = p.gl_dev; a.weight = p.weight;
-  const int threads = ((p.batch + 31) / 32) * 32;
-  msssim_finalize_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const size_t fin_smem = size_t(3) * p.nscales * p.batch * p.channels * sizeof(float);
+  XMM_REQUIRE(fin_smem <= 40 * 1024, "msssim_finalize: batch*channels=%d too large for the single-block reduction",
+              p.batch * p.channels);
+  msssim_finalize_kernel<<<1, 256, fin_smem, static_cast<cudaStream_t>(stream)>>>(a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
 }
