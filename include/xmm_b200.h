@@ -102,6 +102,9 @@ typedef struct {
   int pixel_shuffle;  /* 1: out is [batch][2*height][2*width][out_ctot], cout/4 channels;
                          2: inverse -- out is [batch][height/2][width/2][out_ctot], 4*cout ch. */
   int tap_mode;       /* 0 = library default; 1..3 force a haloed-tap-view layout, 4 the column-scatter form (probe only) */
+  float* colsum;      /* optional (cout == 32): colsum[n] += colsum_scale * sum over all pixels of the value written
+                         to channel n -- the bias gradient whose integrand this data-gradient layer produces       */
+  float colsum_scale;
 } xmm_conv3x3_params;
 
 int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);

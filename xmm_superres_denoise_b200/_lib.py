@@ -36,7 +36,7 @@ class Conv3x3Params(Structure):
                 ("r1", c_void_p), ("r1_ctot", c_int), ("r1_coff", c_int), ("s1", c_float),
                 ("r2", c_void_p), ("r2_ctot", c_int), ("r2_coff", c_int), ("s2", c_float),
                 ("out", c_void_p), ("out_ctot", c_int), ("out_coff", c_int),
-                ("pixel_shuffle", c_int), ("tap_mode", c_int)]
+                ("pixel_shuffle", c_int), ("tap_mode", c_int), ("colsum", c_void_p), ("colsum_scale", c_float)]
 
 
 class NormalizeParams(Structure):

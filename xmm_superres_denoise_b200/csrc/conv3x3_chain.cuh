@@ -234,6 +234,7 @@ conv3x3_chain_kernel(const __grid_constant__ ChainTmaps tmaps, const __grid_cons
         atomicAdd(done + strip, 1);
       }
     }
+    if (L.epi.colsum != nullptr) colsum_flush<Cfg::kWarpCols>(L.epi, w.csum, w.col_w, lane);
     if (args.prof != nullptr && warp == 2 && lane == 0) {
       args.prof[size_t(blockIdx.x) * 4 + 2] = epi_idle;
       args.prof[size_t(blockIdx.x) * 4 + 3] = ntiles;

@@ -161,6 +161,7 @@ struct DxEpiWarp {
   uint32_t mail;       // shared-memory address of this warp's mailboxes (+ this lane's half-warp row)
   uint8_t* out_tile;   // this warp's two staging tiles
   float bias[Cfg::kWarpCols];
+  float csum[Cfg::kWarpCols];  // fused bias gradient: this lane's running column sums (ConvEpilogue::colsum)
   int par;             // tile parity (mailbox / staging double buffering)
   __device__ __forceinline__ void init(int warp, int lane_, const float* bias_s, uint8_t* out_s, uint8_t* mail_s) {
     lane = lane_;
@@ -178,7 +179,10 @@ struct DxEpiWarp {
     out_tile = out_s + ew * 2 * Cfg::kWarpOutBytes;
     par = 0;
 #pragma unroll
-    for (int i = 0; i < Cfg::kWarpCols; ++i) bias[i] = bias_s[col_w + i];
+    for (int i = 0; i < Cfg::kWarpCols; ++i) {
+      bias[i] = bias_s[col_w + i];
+      csum[i] = 0.f;
+    }
   }
   // mailbox slot: kind 0 = D_0 of column 15, kind 1 = unfinished column 15
   __device__ __forceinline__ uint32_t slot(int parity, int kind) const {
@@ -272,11 +276,15 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
         st.chunk0 = uint32_t(col / 8);
         st.xor_mask = NT == 32 ? uint32_t((ps >> 1) & 3) : uint32_t(ps & 7);
         conv_epilogue_math<NT, 16>(epi, nullptr, v, col, b, y, x, H, W, side_tiles ? &st : nullptr);
+        if (epi.colsum != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w.csum[cc * 16 + i] += v[i];
+        }
         const int p = (w.lane >> 4) * kDxTileW + ((w.pcol + 1) & 15);  // box pixel: lane 15 is the box's column 0
         *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2)) = pack8(v);
         *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2 + 1)) = pack8(v + 8);
       } else {
-        conv_epilogue_cols<NT, 16>(epi, nullptr, v, col, b, y, x, H, W);
+        conv_epilogue_cols<NT, 16>(epi, nullptr, v, col, b, y, x, H, W, epi.colsum != nullptr ? &w.csum[cc * 16] : nullptr);
       }
     }
     // End of the strip: column 15 of the last tile has no right neighbour (D_2[W] = 0).
@@ -287,7 +295,8 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
         const float4 t4 = *reinterpret_cast<const float4*>(__cvta_shared_to_generic(size_t(b_w) + size_t(j * 16)));
         f[4 * j] = t4.x; f[4 * j + 1] = t4.y; f[4 * j + 2] = t4.z; f[4 * j + 3] = t4.w;
       }
-      conv_epilogue_cols<NT, 16>(epi, nullptr, f, col, b, y, tx * kDxTileW + 15, H, W);
+      conv_epilogue_cols<NT, 16>(epi, nullptr, f, col, b, y, tx * kDxTileW + 15, H, W,
+                                 epi.colsum != nullptr ? &w.csum[cc * 16] : nullptr);
     }
   }
   if (use_tma) {
@@ -523,6 +532,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       }
     }
     if (ptx::elect_one()) ptx::bulk_wait<0>();  // this warp's stores complete before the CTA (and its smem) goes away
+    if (args.epi.colsum != nullptr) colsum_flush<Cfg::kWarpCols>(args.epi, w.csum, w.col_w, lane);
     if (warp == 2 && lane == 0) { XMM_PROF_FLUSH(4); XMM_PROF_FLUSH(5); }
   }
 

@@ -72,6 +72,10 @@ struct ConvEpilogue {
   // Image mode (conv_last, generator_rrdb.py:48-54,107-108,132-135, on the tensor cores): img_out != nullptr.
   // The packed layer holds bf16(w) in rows [0, img_cout) and the low-order halves bf16(w - bf16(w)) in rows
   // [16, 16 + img_cout); out[b][o][y][x] = clamp?(acc[o] + acc[16+o] + bias[o] + img_res[...]) in fp32 NCHW.
+  // Optional fused bias gradient: colsum[n] += colsum_scale * sum over the launch's pixels of the value written to
+  // channel n (the data gradient dY a layer produces is also the bias gradient's integrand).  Cout = 32 kernels.
+  float* colsum;
+  float colsum_scale;
   float* img_out;
   const float* img_res;
   float* img_pre;   // optional copy of the un-clamped value (backward clamp gate)
@@ -210,8 +214,13 @@ __device__ __forceinline__ void conv_epilogue_math(const ConvEpilogue& e, const 
 // Epilogue for NC accumulator columns [col0, col0+NC) of one pixel: arithmetic + direct bf16 store.
 template <int NT, int NC>
 __device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const float* __restrict__ bias_s,
-                                                   float (&v)[NC], int col0, int b, int y, int x, int H, int W) {
+                                                   float (&v)[NC], int col0, int b, int y, int x, int H, int W,
+                                                   float* csum = nullptr) {
   conv_epilogue_math<NT, NC>(e, bias_s, v, col0, b, y, x, H, W);
+  if (csum != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) csum[i] += v[i];
+  }
   const size_t pix = (size_t(b) * H + y) * W + x;
   uint4* op;
   if (e.pixel_shuffle == 2) {
@@ -237,11 +246,23 @@ __device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const 
 template <int NT>
 __device__ __forceinline__ void conv_epilogue_32(const ConvEpilogue& e, const float* __restrict__ bias_s,
                                                  uint32_t (&acc)[32], int col0, int b, int y, int x,
-                                                 int H, int W) {
+                                                 int H, int W, float* csum = nullptr) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-  conv_epilogue_cols<NT, 32>(e, bias_s, v, col0, b, y, x, H, W);
+  conv_epilogue_cols<NT, 32>(e, bias_s, v, col0, b, y, x, H, W, csum);
+}
+
+// End of a warp's life: add its lanes' column sums and publish them (one atomic per column and warp).
+template <int NC>
+__device__ __forceinline__ void colsum_flush(const ConvEpilogue& e, float (&csum)[NC], int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    float x = csum[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if (lane == 0) atomicAdd(e.colsum + col0 + i, e.colsum_scale * x);
+  }
 }
 
 template <int KC, int NT, int MODE>
@@ -402,6 +423,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     int obuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool do_csum = NT == 32 && args.epi.colsum != nullptr;
+    float csum[NT == 32 ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (NT == 32 ? 32 : 1); ++i) csum[i] = 0.f;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
@@ -451,11 +476,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]);
             conv_epilogue_math<NT, 32>(args.epi, bias_s, v, cc * 32, b, y, x, args.height, args.width);
+            if (NT == 32 && do_csum) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) csum[NT == 32 ? i : 0] += v[i];
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(stage + lane * (NT * 2) + (((uint32_t(cc * 4 + j)) ^ sw_xor) << 4)) = pack8(v + j * 8);
           } else {
-            conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
+            if (NT == 32) {
+              float (&cs32)[32] = reinterpret_cast<float (&)[32]>(csum);
+              conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width,
+                                   do_csum ? &cs32[0] : nullptr);
+            } else {
+              conv_epilogue_32<NT>(args.epi, bias_s, accr, cc * 32, b, y, x, args.height, args.width);
+            }
           }
         }
       }
@@ -473,6 +508,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       if (acc == 0) acc_phase ^= 1u;
     }
     if (use_tma && ptx::elect_one()) ptx::bulk_wait<0>();  // stores complete before the CTA (and its smem) goes away
+    if (NT == 32 && do_csum) {
+      float (&cs32)[32] = reinterpret_cast<float (&)[32]>(csum);
+      colsum_flush<32>(args.epi, cs32, 0, lane);
+    }
     if (warp == 2 && lane == 0) { XMM_PROF_FLUSH(4); XMM_PROF_FLUSH(5); }
   }
 

@@ -152,21 +152,38 @@ class TrainEngine(RRDBEngine):
         f, kc, a = self.nf, self.kc, self.arena
         act, ring = bufs["act"], bufs["ring"]
         A, G = act[3 * i + r], ring[r]
+        rdb = self._rdb(i, r)
         layers = []
-        for j in range(4, 0, -1):  # dY_j = LeakyReLU'(x_j) * sum_k dgrad_k(dY_k)
+        for j in range(4, 0, -1):  # dY_j = LeakyReLU'(x_j) * sum_k dgrad_k(dY_k); its column sums are conv_j's bias grad
             layers.append(((G, j * f, (5 - j) * f, a.ptr(f"d.{i}.{r}.{j}"), kc, f, G, (j - 1) * f),
-                           dict(mask=A, mask_coff=j * f, mask_slope=0.2)))
-        # gradient of the block input: + skip connection(s)
+                           dict(mask=A, mask_coff=j * f, mask_slope=0.2,
+                                **self._bias_sum(grads, getattr(rdb, f"conv{j}"), 1.0))))
+        # gradient of the block input: + skip connection(s).  The result is the output gradient g of the NEXT block to be
+        # processed, i.e. the integrand of that block's conv5 bias gradient (scaled by its folded residual factor).
         if r == 2:    # out_rrdb = 0.2 * out_rdb3 + x_rrdb ; G[4] holds E_i = dL/d(out_rrdb)
-            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[1], 4 * f), dict(r1=G, r1_coff=4 * f, s1=0.2))
+            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[1], 4 * f),
+                    dict(r1=G, r1_coff=4 * f, s1=0.2, **self._bias_sum(grads, self._rdb(i, 1).conv5, 0.2)))
         elif r == 1:
-            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[0], 4 * f), dict(r1=G, r1_coff=4 * f, s1=1.0))
+            last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, ring[0], 4 * f),
+                    dict(r1=G, r1_coff=4 * f, s1=1.0, **self._bias_sum(grads, self._rdb(i, 0).conv5, 0.2)))
         else:         # RDB1: + g_1 + E_i (RRDB skip); result is E_{i-1}, or dL/d(fea) through the trunk for i == 0
             out, ocoff = (ring[2], 4 * f) if i > 0 else (d_fea, 0)
+            extra = self._bias_sum(grads, self._rdb(i - 1, 2).conv5, 0.04) if i > 0 else {}
             last = ((G, 0, 5 * f, a.ptr(f"d.{i}.{r}.0"), kc, f, out, ocoff),
-                    dict(r1=G, r1_coff=4 * f, s1=1.0, r2=ring[2], r2_coff=4 * f, s2=1.0))
+                    dict(r1=G, r1_coff=4 * f, s1=1.0, r2=ring[2], r2_coff=4 * f, s2=1.0, **extra))
         layers.append(last)
         ops.conv3x3_chain(layers, self.chain_mode)
+
+    def _rdb(self, i: int, r: int):
+        rrdb = self.gen.rrdb[i]
+        return (rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)[r]
+
+    def _bias_sum(self, grads, conv, scale: float) -> dict:
+        """conv3x3 keywords that make the producing layer accumulate `conv`'s bias gradient (views of the
+        zero-initialised flat gradient buffer)."""
+        if conv.bias is None:
+            return {}
+        return dict(colsum=self._gv(grads, conv.bias), colsum_scale=scale)
 
     def _rdb_wgrad(self, i: int, r: int, bufs, grads) -> None:
         f = self.nf
@@ -175,7 +192,7 @@ class TrainEngine(RRDBEngine):
         A, G = bufs["act"][3 * i + r], bufs["ring"][r]
         s5 = 0.04 if r == 2 else 0.2
         roles = [(3 * d, 3, 0, 2, 0, 5 * f) for d in range(3)] + [(0, 9, 4 * f, 1, 4 * f, f)]
-        dsts, bias_segs = [], []
+        dsts = []
         for k in range(1, 6):
             conv = getattr(rdb, f"conv{k}")
             dw = self._gv(grads, conv.weight)
@@ -184,10 +201,7 @@ class TrainEngine(RRDBEngine):
                 dsts.append((dw, f, k * f, 0, min(k * f, 4 * f), d, 0, (k - 1) * f, sc, 0, 0))
             if k == 5:
                 dsts.append((dw, f, 5 * f, 4 * f, 5 * f, 3, 0, 0, sc, 0, 0))
-            if conv.bias is not None:  # accumulate: the flat gradient buffer starts at zero
-                bias_segs.append(((k - 1) * f, f, self._gv(grads, conv.bias), sc, True))
-        if bias_segs:
-            ops.colsum_multi(G, bias_segs)  # the five bias gradients: one pass over the block's gradient buffer
+        # (bias gradients: accumulated by the conv launches that produced G's slots -- _rdb_backward / backward)
         ops.conv3x3_wgrad(A, G, roles, dsts)
 
     def backward(self, bufs, generation: int, x: torch.Tensor, gout: torch.Tensor, need_x_grad: bool,
@@ -232,7 +246,8 @@ class TrainEngine(RRDBEngine):
         ring = bufs["ring"]
         d_fea = bufs["d_fea"]
         if self.nb > 0:
-            ops.conv3x3(d_trunk, 0, f, a.ptr("d.trunk"), kc, f, ring[2], 4 * f)  # E_{nb-1}
+            ops.conv3x3(d_trunk, 0, f, a.ptr("d.trunk"), kc, f, ring[2], 4 * f,  # E_{nb-1} = g of the last RDB3
+                        **self._bias_sum(grads, self._rdb(self.nb - 1, 2).conv5, 0.04))
             for i in range(self.nb - 1, -1, -1):
                 for r in (2, 1, 0):
                     self._rdb_backward(i, r, bufs, grads, d_fea)

@@ -38,7 +38,8 @@ def _conv3x3_params(p: Conv3x3Params, inp: torch.Tensor, in_coff: int, cin: int,
                     r1: Optional[torch.Tensor] = None, r1_coff: int = 0, s1: float = 0.0,
                     r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
                     mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
-                    pixel_shuffle: int = 0, tap_mode: int = 0) -> None:
+                    pixel_shuffle: int = 0, tap_mode: int = 0, colsum: Optional[torch.Tensor] = None,
+                    colsum_scale: float = 1.0) -> None:
     _nhwc(inp, "conv3x3 input")
     _nhwc(out, "conv3x3 output")
     b, h, w, ctot = inp.shape
@@ -66,13 +67,19 @@ def _conv3x3_params(p: Conv3x3Params, inp: torch.Tensor, in_coff: int, cin: int,
     p.out, p.out_ctot, p.out_coff = out.data_ptr(), out.shape[3], out_coff
     p.pixel_shuffle = pixel_shuffle
     p.tap_mode = tap_mode
+    if colsum is not None:
+        _lib.require_cuda_tensor(colsum, torch.float32, "conv3x3 colsum")
+        if colsum.numel() != cout:
+            raise RuntimeError("conv3x3 colsum: one float per output channel")
+        p.colsum, p.colsum_scale = colsum.data_ptr(), colsum_scale
 
 
 def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, cout: int,
             out: torch.Tensor, out_coff: int, **kw) -> None:
     """out[..., out_coff:out_coff+cout] = epilogue(conv3x3(inp[..., in_coff:in_coff+cin])).
 
-    Keywords: lrelu, s0, r1/r1_coff/s1, r2/r2_coff/s2, mask/mask_coff/mask_slope, pixel_shuffle, tap_mode.
+    Keywords: lrelu, s0, r1/r1_coff/s1, r2/r2_coff/s2, mask/mask_coff/mask_slope, pixel_shuffle, tap_mode,
+    colsum/colsum_scale (fused bias gradient: colsum += scale * column sums of the written values).
     See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
     p = Conv3x3Params()
     _conv3x3_params(p, inp, in_coff, cin, wblob_ptr, kc, cout, out, out_coff, **kw)
