@@ -220,6 +220,10 @@ typedef struct {
   int tap_begin, tap_count; /* taps [tap_begin, tap_begin+tap_count) of the 9, tap = 3*dy+dx   */
   int x_c0, x_boxes;        /* M tile: X channels [x_c0, x_c0 + 64*x_boxes) (x_boxes 1 or 2)    */
   int y_c0, n;              /* N tile: dY channels [y_c0, y_c0 + n), n multiple of 16, <= 192   */
+  int mode;                 /* 0: as above.  1: "stacked" 32-channel role -- M = dY channels [y_c0, y_c0 + 64*x_boxes),
+                               N = 96 = X channels [x_c0, x_c0+32) at dx = 0,1,2; tap_begin 0, tap_count 3 (filter
+                               rows).  Destinations of such a role: lane0 = first dY channel - y_c0,
+                               col0 = i_begin - x_c0; all 9 taps are written.                                  */
 } xmm_wgrad_role;
 
 typedef struct {

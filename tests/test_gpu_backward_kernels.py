@@ -26,23 +26,26 @@ def _ref_wgrad(x_nhwc, dy_nhwc):
     return w.grad
 
 
-def test_wgrad_dense_block_roles(dev):
+@pytest.mark.parametrize("stacked", [0, 1])
+def test_wgrad_dense_block_roles(dev, stacked):
     """X = 160-channel activation buffer, dY = 160-channel gradient buffer (slot k-1 = dY_k):
-    3 main roles (x0..x3 against all dY) + tail role (x4 against dY_5), 16 destinations."""
+    3 main roles (x0..x3 against all dY) + tail role (x4 against dY_5), 16 destinations.  The tail either as nine
+    N=32 taps or as a "stacked" role (operands swapped, three dx taps per MMA as overlapping swizzle atoms)."""
     from xmm_superres_denoise_b200 import ops
 
     g = torch.Generator().manual_seed(0)
     b, h, w, f = 2, 40, 24, 32
     x = torch.randn(b, h, w, 5 * f, generator=g).to(torch.bfloat16)
     dy = (torch.randn(b, h, w, 5 * f, generator=g) * 0.1).to(torch.bfloat16)
-    roles = [(3 * d, 3, 0, 2, 0, 160) for d in range(3)] + [(0, 9, 128, 1, 128, 32)]
+    roles = [(3 * d, 3, 0, 2, 0, 160) for d in range(3)]
+    roles.append((0, 3, 128, 1, 96, 96, 1) if stacked else (0, 9, 128, 1, 128, 32))
     dws = [torch.full((f, k * f, 3, 3), 7.0, device=dev) for k in range(1, 6)]
     dsts = []
     for k in range(1, 6):
         scale = 0.2 if k == 5 else 1.0
         for d in range(3):
             dsts.append((dws[k - 1], f, k * f, 0, min(k * f, 128), d, 0, (k - 1) * f, scale, 0, 0))
-    dsts.append((dws[4], f, 5 * f, 128, 160, 3, 0, 0, 0.2, 0, 0))
+    dsts.append((dws[4], f, 5 * f, 128, 160, 3, 32 if stacked else 0, 0, 0.2, 0, 0))
     ops.conv3x3_wgrad(x.to(dev), dy.to(dev), roles, dsts)
     torch.cuda.synchronize()
     for k in range(1, 6):
@@ -50,8 +53,9 @@ def test_wgrad_dense_block_roles(dev):
         assert rel_l2(dws[k - 1].cpu(), want) < 2e-3, k
 
 
+@pytest.mark.parametrize("stacked", [0, 1])
 @pytest.mark.parametrize("n,perm", [(32, 0), (128, 1)])
-def test_wgrad_single_conv(dev, n, perm):
+def test_wgrad_single_conv(dev, n, perm, stacked):
     """F -> n convolution whose input tensor has only F=32 channels (TMA zero-fills channels 32..63)."""
     from xmm_superres_denoise_b200 import ops
 
@@ -61,7 +65,10 @@ def test_wgrad_single_conv(dev, n, perm):
     dy = (torch.randn(b, h, w, n, generator=g) * 0.1).to(torch.bfloat16)
     dw = torch.zeros(n, f, 3, 3, device=dev)
     dw += 1.0
-    if n == 32:
+    if stacked:  # operands swapped: lanes = the n dY channels (1 or 2 boxes), columns = 3 dx taps x 32 X channels
+        roles = [(0, 3, 0, 1 if n <= 64 else 2, 0, 96, 1)]
+        dsts = [(dw, n, f, 0, f, 0, 0, 0, 1.0, 1, perm)]
+    elif n == 32:
         roles = [(0, 9, 0, 1, 0, 32)]
         dsts = [(dw, n, f, 0, f, 0, 0, 0, 1.0, 1, perm)]
     else:

@@ -64,7 +64,7 @@ class ConvLastParams(Structure):
 
 class WgradRole(Structure):
     _fields_ = [("tap_begin", c_int), ("tap_count", c_int), ("x_c0", c_int), ("x_boxes", c_int), ("y_c0", c_int),
-                ("n", c_int)]
+                ("n", c_int), ("mode", c_int)]
 
 
 class WgradDst(Structure):

@@ -16,7 +16,14 @@
 // Dense-block use (F = 32): X = the 5F-channel activation buffer, dY = the 5F-channel
 // gradient buffer (slot k-1 = dY_k).  Role "main(dy)": X channels 0..127 (x0..x3) against all
 // 160 dY columns, 3 taps -> 480 TMEM columns; role "tail": X channels 128..159 (x4) against
-// dY_5, 9 taps -> 288 columns.  Blocks (x_j, dY_k) with j >= k are computed but unused.
+// dY_5.  Blocks (x_j, dY_k) with j >= k are computed but unused.
+//
+// The tail is a 32 x 32 product per tap -- nine N = 32 MMAs at the ~47-cycle floor of an M = 128 instruction would
+// cost more than half of the main roles' 3 x 3 N = 160 MMAs for 1/15 of the work.  Role mode 1 ("stacked") swaps the
+// operands and puts the three dx taps of a filter row into ONE instruction: A = the dY box (M = output channels),
+// B = a 32-channel SWIZZLE_64B patch of X whose N = 96 columns are three swizzle atoms placed ONE PIXEL (64 bytes)
+// apart (LBO = 64: the atoms overlap; the UMMA address generator is linear and the swizzle is a function of the
+// absolute shared-memory address, so atom j simply reads the patch shifted by j pixels).  3 MMAs instead of 9.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -33,6 +40,7 @@ constexpr int kWgTileH = 8;
 constexpr int kWgMaxStages = 6;
 constexpr int kWgBoxXBytes = 13312;   // (8+2)*10 pixels * 128 B = 12800, padded to a 1024-B multiple
 constexpr int kWgBoxYBytes = 8192;    // 8*8 pixels * 128 B
+constexpr int kWgBoxX32Bytes = 7168;  // mode 1: (8+2)*10 pixels * 64 B = 6400, padded to a 1024-B multiple
 constexpr int kWgMaxRoles = 4;
 constexpr int kWgWsFloatsPerCta = 128 * 512;
 
@@ -40,10 +48,13 @@ struct WgradRole {
   int cta_begin, cta_count;
   int tap_begin, tap_count;
   int x_c0;      // first X channel of the M tile (box of 64 channels; beyond-ctot channels read as 0)
-  int x_boxes;   // 1 (M rows 64..127 alias rows 0..63) or 2
+  int x_boxes;   // boxes of the M operand: 1 (M rows 64..127 alias rows 0..63) or 2
   int y_c0;      // first dY channel of the N tile
   int y_boxes;   // ceil(n / 64)
   int n;         // N of the MMA (multiple of 16, <= 192)
+  int mode;      // 0: A = X taps, B = dY.  1: stacked -- A = dY channels [y_c0, y_c0 + 64 * x_boxes),
+                 //    B = X channels [x_c0, x_c0+32) at dx = 0,1,2 (n = 96); tap_count = 3 filter rows, accumulator
+                 //    column = dy * 96 + dx * 32 + (x channel - x_c0), lane = dY channel - y_c0
 };
 
 struct WgradArgs {
@@ -57,7 +68,7 @@ struct WgradArgs {
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y,
-                const WgradArgs args) {
+                const __grid_constant__ CUtensorMap tmap_x32, const WgradArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kWgMaxStages], empty_bar[kWgMaxStages], done_bar;
@@ -71,13 +82,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   for (int r = 0; r < args.nroles; ++r)
     if (int(blockIdx.x) >= args.roles[r].cta_begin && int(blockIdx.x) < args.roles[r].cta_begin + args.roles[r].cta_count) ri = r;
   const WgradRole role = args.roles[ri];
-  const int stage_bytes = role.x_boxes * kWgBoxXBytes + role.y_boxes * kWgBoxYBytes;
+  const int stage_bytes = role.mode == 1 ? role.x_boxes * kWgBoxYBytes + kWgBoxX32Bytes
+                                         : role.x_boxes * kWgBoxXBytes + role.y_boxes * kWgBoxYBytes;
   const int first_tile = int(blockIdx.x) - role.cta_begin;
   const bool has_work = first_tile < args.num_tiles;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_y);
+    ptx::prefetch_tmap(&tmap_x32);
     for (int s = 0; s < args.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -102,8 +115,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int ty = r / args.tiles_x;
         const int tx = r - ty * args.tiles_x;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-        ptx::mbar_expect_tx(&full_bar[stage], uint32_t(role.x_boxes * (kWgTileH + 2) * (kTileW + 2) * 128 + role.y_boxes * kWgBoxYBytes));
         uint8_t* dst = smem + size_t(stage) * stage_bytes;
+        if (role.mode == 1) {
+          ptx::mbar_expect_tx(&full_bar[stage],
+                              uint32_t(role.x_boxes * kWgBoxYBytes + (kWgTileH + 2) * (kTileW + 2) * 64));
+          for (int yb = 0; yb < role.x_boxes; ++yb)
+            ptx::tma_load_4d(dst + yb * kWgBoxYBytes, &tmap_y, &full_bar[stage], role.y_c0 + 64 * yb, tx * kTileW,
+                             ty * kWgTileH, b);
+          ptx::tma_load_4d(dst + role.x_boxes * kWgBoxYBytes, &tmap_x32, &full_bar[stage], role.x_c0, tx * kTileW - 1,
+                           ty * kWgTileH - 1, b);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          continue;
+        }
+        ptx::mbar_expect_tx(&full_bar[stage], uint32_t(role.x_boxes * (kWgTileH + 2) * (kTileW + 2) * 128 + role.y_boxes * kWgBoxYBytes));
         for (int xb = 0; xb < role.x_boxes; ++xb)
           ptx::tma_load_4d(dst + xb * kWgBoxXBytes, &tmap_x, &full_bar[stage], role.x_c0 + 64 * xb, tx * kTileW - 1,
                            ty * kWgTileH - 1, b);
@@ -129,17 +156,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         ptx::tc_fence_after();
         const uint32_t x_addr = ptx::smem_u32(smem + size_t(stage) * stage_bytes);
         const uint32_t y_addr = x_addr + uint32_t(role.x_boxes * kWgBoxXBytes);
+        if (role.mode == 1) {  // stage = [dY box(es)][X32 patch]
+          const uint32_t p_addr = x_addr + uint32_t(role.x_boxes * kWgBoxYBytes);
+          const uint32_t m_lbo = role.x_boxes > 1 ? uint32_t(kWgBoxYBytes) : 0u;
 #pragma unroll 1
-        for (int s = 0; s < kWgTileH / 2; ++s) {  // 16 pixels (two tile rows) per MMA
-          const uint64_t bdesc = ptx::umma_smem_desc(y_addr + uint32_t(s * 2 * kTileW * 128), kWgBoxYBytes,
-                                                     kTileW * 128, ptx::UMMA_SW128);
+          for (int s = 0; s < kWgTileH / 2; ++s) {
+            const uint64_t adesc =
+                ptx::umma_smem_desc(x_addr + uint32_t(s * 2 * kTileW * 128), m_lbo, kTileW * 128, ptx::UMMA_SW128);
 #pragma unroll 1
-          for (int t = 0; t < role.tap_count; ++t) {
-            const int tap = role.tap_begin + t;
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_addr = x_addr + uint32_t(((2 * s + dy) * (kTileW + 2) + dx) * 128);
-            const uint64_t adesc = ptx::umma_smem_desc(a_addr, a_lbo, (kTileW + 2) * 128, ptx::UMMA_SW128);
-            ptx::umma_ss(tmem_base + uint32_t(t * role.n), adesc, bdesc, idesc, (first && s == 0) ? 0u : 1u);
+            for (int dy = 0; dy < 3; ++dy) {
+              const uint64_t bdesc = ptx::umma_smem_desc(p_addr + uint32_t((2 * s + dy) * (kTileW + 2) * 64), 64,
+                                                         (kTileW + 2) * 64, ptx::UMMA_SW64);
+              ptx::umma_ss(tmem_base + uint32_t(dy * role.n), adesc, bdesc, idesc, (first && s == 0) ? 0u : 1u);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int s = 0; s < kWgTileH / 2; ++s) {  // 16 pixels (two tile rows) per MMA
+            const uint64_t bdesc = ptx::umma_smem_desc(y_addr + uint32_t(s * 2 * kTileW * 128), kWgBoxYBytes,
+                                                       kTileW * 128, ptx::UMMA_SW128);
+#pragma unroll 1
+            for (int t = 0; t < role.tap_count; ++t) {
+              const int tap = role.tap_begin + t;
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const uint32_t a_addr = x_addr + uint32_t(((2 * s + dy) * (kTileW + 2) + dx) * 128);
+              const uint64_t adesc = ptx::umma_smem_desc(a_addr, a_lbo, (kTileW + 2) * 128, ptx::UMMA_SW128);
+              ptx::umma_ss(tmem_base + uint32_t(t * role.n), adesc, bdesc, idesc, (first && s == 0) ? 0u : 1u);
+            }
           }
         }
         first = false;
@@ -178,7 +221,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
 // One destination tensor of the reduction: dW (fp32 OIHW [o_count][i_total][3][3]) gathers
 //   dW[o][i][tap] (+)= scale * sum over the role's CTAs of ws[cta][lane = i - x_c0][(tap - tap_begin) * n + y_col0 + o]
-// for i in [i_begin, i_end), from the role that owns (tap, i).
+// for i in [i_begin, i_end), from the role that owns (tap, i).  For a stacked role (mode 1) lanes are output channels:
+//   ws[cta][lane0 + o][(tap / 3) * 96 + (tap % 3) * 32 + col0 + (i - i_begin)],  all 9 taps.
 struct WgradDst {
   float* dw;
   int o_count, i_total;
@@ -203,18 +247,20 @@ __global__ void wgrad_reduce_kernel(const WgradReduceArgs a, int num_tiles) {
   const WgradDst d = a.dst[blockIdx.y];
   const WgradRole role = a.roles[d.role];
   const int ni = d.i_end - d.i_begin;
-  const int total = d.o_count * ni * role.tap_count;
+  const int ntap = role.mode == 1 ? 9 : role.tap_count;
+  const int total = d.o_count * ni * ntap;
   int active = role.cta_count < num_tiles ? role.cta_count : num_tiles;  // CTAs beyond num_tiles wrote nothing
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int o = e % d.o_count;
     const int rest = e / d.o_count;
     const int i = rest % ni;
     const int t = rest / ni;
-    const size_t off = size_t(d.lane0 + i) * 512 + size_t(t * role.n + d.col0 + o);
+    const size_t off = role.mode == 1 ? size_t(d.lane0 + o) * 512 + size_t((t / 3) * role.n + (t % 3) * 32 + d.col0 + i)
+                                      : size_t(d.lane0 + i) * 512 + size_t(t * role.n + d.col0 + o);
     float s = 0.f;
     for (int c = 0; c < active; ++c) s += a.ws[size_t(role.cta_begin + c) * kWgWsFloatsPerCta + off];
     const int oo = d.perm ? shuffle_perm(o, d.o_count / 4) : o;
-    float* p = d.dw + (size_t(oo) * d.i_total + (d.i_begin + i)) * 9 + (role.tap_begin + t);
+    float* p = d.dw + (size_t(oo) * d.i_total + (d.i_begin + i)) * 9 + (role.mode == 1 ? t : role.tap_begin + t);
     *p = d.accumulate ? (*p + d.scale * s) : d.scale * s;
   }
 }

@@ -683,6 +683,15 @@ extern "C" size_t xmm_wgrad_workspace_bytes(void) {
   return size_t(sms) * kWgWsFloatsPerCta * sizeof(float);
 }
 
+// CTA share of a stacked role relative to the max(n/2, 47)-cycles-per-MMA model (XMM_WG_STACKED_COST overrides).
+static double wg_stacked_cost_scale() {
+  static const double v = [] {
+    const char* e = getenv("XMM_WG_STACKED_COST");
+    return e ? atof(e) : 1.3;
+  }();
+  return v;
+}
+
 extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   XMM_REQUIRE(pp != nullptr, "wgrad: null params");
   const xmm_wgrad_params& p = *pp;
@@ -695,6 +704,11 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   XMM_REQUIRE(p.nroles >= 1 && p.nroles <= kWgMaxRoles && p.ndst >= 1 && p.ndst <= 16, "wgrad: %d roles / %d dsts",
               p.nroles, p.ndst);
   XMM_REQUIRE(dev.sm_count >= p.nroles, "wgrad: fewer SMs than roles");
+  static const int max_ctas_env = [] {  // experiments only: leave SMs idle to separate per-SM from chip-wide limits
+    const char* e = getenv("XMM_WG_MAX_CTAS");
+    return e ? atoi(e) : 0;
+  }();
+  if (max_ctas_env >= p.nroles && max_ctas_env < dev.sm_count) dev.sm_count = max_ctas_env;
   WgradArgs a{};
   WgradReduceArgs ra{};
   a.nroles = ra.nroles = p.nroles;
@@ -705,16 +719,21 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
     XMM_REQUIRE(q.tap_begin >= 0 && q.tap_count >= 1 && q.tap_begin + q.tap_count <= 9, "wgrad: role %d taps", r);
     XMM_REQUIRE(q.n >= 16 && q.n % 16 == 0 && q.n <= 192 && q.tap_count * q.n <= 512,
                 "wgrad: role %d needs %d x %d TMEM columns (max 512)", r, q.tap_count, q.n);
+    XMM_REQUIRE(q.mode == 0 || q.mode == 1, "wgrad: role %d mode %d", r, q.mode);
+    if (q.mode == 1)
+      XMM_REQUIRE(q.tap_begin == 0 && q.tap_count == 3 && q.n == 96 && q.x_c0 + 32 <= p.x_ctot && q.y_c0 < p.dy_ctot,
+                  "wgrad: stacked role %d must be 3 filter rows x (3 dx x 32 X channels)", r);
     XMM_REQUIRE((q.x_boxes == 1 || q.x_boxes == 2) && q.x_c0 % 8 == 0 && q.y_c0 % 8 == 0 && q.x_c0 < p.x_ctot &&
-                    q.y_c0 + q.n <= ((p.dy_ctot + 63) / 64) * 64 + 64,
+                    (q.mode == 1 || q.y_c0 + q.n <= ((p.dy_ctot + 63) / 64) * 64 + 64),
                 "wgrad: role %d channel windows", r);
     WgradRole& w = a.roles[r];
     w.tap_begin = q.tap_begin; w.tap_count = q.tap_count; w.x_c0 = q.x_c0; w.x_boxes = q.x_boxes;
-    w.y_c0 = q.y_c0; w.n = q.n; w.y_boxes = (q.n + 63) / 64;
+    w.y_c0 = q.y_c0; w.n = q.n; w.y_boxes = (q.n + 63) / 64; w.mode = q.mode;
     const double per_mma = q.n / 2.0 > 47.0 ? q.n / 2.0 : 47.0;  // measured tcgen05 floor, profiles/r01_probe1
-    cost[r] = q.tap_count * per_mma;
+    cost[r] = q.tap_count * per_mma * (q.mode == 1 ? wg_stacked_cost_scale() : 1.0);
     total += cost[r];
-    const size_t st = size_t(w.x_boxes) * kWgBoxXBytes + size_t(w.y_boxes) * kWgBoxYBytes;
+    const size_t st = q.mode == 1 ? size_t(w.x_boxes) * kWgBoxYBytes + size_t(kWgBoxX32Bytes)
+                                  : size_t(w.x_boxes) * kWgBoxXBytes + size_t(w.y_boxes) * kWgBoxYBytes;
     if (st > max_stage) max_stage = st;
   }
   int assigned = 0;
@@ -750,16 +769,23 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   for (int i = 0; i < p.ndst; ++i) {
     const xmm_wgrad_dst& q = p.dst[i];
     XMM_REQUIRE(q.dw && q.role >= 0 && q.role < p.nroles && q.i_begin >= 0 && q.i_end > q.i_begin &&
-                    q.i_end <= q.i_total && q.lane0 >= 0 && q.lane0 + (q.i_end - q.i_begin) <= 128 && q.col0 >= 0 &&
-                    q.col0 + q.o_count <= p.roles[q.role].n,
+                    q.i_end <= q.i_total && q.lane0 >= 0 && q.col0 >= 0,
                 "wgrad: destination %d is inconsistent with its role", i);
+    if (p.roles[q.role].mode == 1)
+      XMM_REQUIRE(q.lane0 + q.o_count <= 64 * p.roles[q.role].x_boxes && q.col0 + (q.i_end - q.i_begin) <= 32,
+                  "wgrad: destination %d does not fit its stacked role", i);
+    else
+      XMM_REQUIRE(q.lane0 + (q.i_end - q.i_begin) <= 128 && q.col0 + q.o_count <= p.roles[q.role].n,
+                  "wgrad: destination %d is inconsistent with its role", i);
     WgradDst& d = ra.dst[i];
     d.dw = q.dw; d.o_count = q.o_count; d.i_total = q.i_total; d.i_begin = q.i_begin; d.i_end = q.i_end;
     d.role = q.role; d.lane0 = q.lane0; d.col0 = q.col0; d.scale = q.scale; d.accumulate = q.accumulate; d.perm = q.perm;
   }
 
-  CUtensorMap tx, ty;
+  CUtensorMap tx, ty, tx32;
   rc = cached_tmap(&tx, p.x, p.batch, p.height, p.width, p.x_ctot, 64, kTileW + 2, kWgTileH + 2);
+  if (rc != XMM_OK) return rc;
+  rc = cached_tmap(&tx32, p.x, p.batch, p.height, p.width, p.x_ctot, 32, kTileW + 2, kWgTileH + 2);  // SWIZZLE_64B
   if (rc != XMM_OK) return rc;
   rc = cached_tmap(&ty, p.dy, p.batch, p.height, p.width, p.dy_ctot, 64, kTileW, kWgTileH);
   if (rc != XMM_OK) return rc;
@@ -770,7 +796,7 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  wgrad_tc_kernel<<<dev.sm_count, kWgThreads, smem, s>>>(tx, ty, a);
+  wgrad_tc_kernel<<<dev.sm_count, kWgThreads, smem, s>>>(tx, ty, tx32, a);
   XMM_CUDA_OK(cudaGetLastError());
   wgrad_reduce_kernel<<<dim3(24, p.ndst), 256, 0, s>>>(ra, a.num_tiles);
   XMM_CUDA_OK(cudaGetLastError());

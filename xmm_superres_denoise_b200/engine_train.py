@@ -134,11 +134,9 @@ class TrainEngine(RRDBEngine):
         f = self.nf
         n = conv.weight.shape[0]
         dw = self._gv(grads, conv.weight)
-        if n == f:
-            ops.conv3x3_wgrad(x, dy, [(0, 9, 0, 1, 0, f)], [(dw, n, f, 0, f, 0, 0, 0, 1.0, 0, perm)])
-        else:  # F -> 4F: one role per filter row (3 taps x 128 columns of TMEM)
-            ops.conv3x3_wgrad(x, dy, [(3 * d, 3, 0, 1, 0, n) for d in range(3)],
-                              [(dw, n, f, 0, f, d, 0, 0, 1.0, 0, perm) for d in range(3)])
+        # F -> F / F -> 4F: one stacked role (M = the n dY channels, N = 3 dx taps x 32 X channels; 3 MMAs per 16
+        # pixels instead of 9 N=32 / N=128 ones with three quarters of the M rows aliased)
+        ops.conv3x3_wgrad(x, dy, [(0, 3, 0, 1 if n <= 64 else 2, 0, 3 * f, 1)], [(dw, n, f, 0, f, 0, 0, 0, 1.0, 0, perm)])
         if conv.bias is not None:
             db = self._gv(grads, conv.bias)
             if perm:
@@ -191,7 +189,9 @@ class TrainEngine(RRDBEngine):
         rdb = (rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)[r]
         A, G = bufs["act"][3 * i + r], bufs["ring"][r]
         s5 = 0.04 if r == 2 else 0.2
-        roles = [(3 * d, 3, 0, 2, 0, 5 * f) for d in range(3)] + [(0, 9, 4 * f, 1, 4 * f, f)]
+        # x0..x3 against all five dY slots, one role per filter row; x4 x dY5 as a stacked role (three dx taps per
+        # MMA, operands swapped: lanes = channels of the [dY4|dY5] box)
+        roles = [(3 * d, 3, 0, 2, 0, 5 * f) for d in range(3)] + [(0, 3, 4 * f, 1, 3 * f, 3 * f, 1)]
         dsts = []
         for k in range(1, 6):
             conv = getattr(rdb, f"conv{k}")
@@ -200,7 +200,7 @@ class TrainEngine(RRDBEngine):
             for d in range(3):
                 dsts.append((dw, f, k * f, 0, min(k * f, 4 * f), d, 0, (k - 1) * f, sc, 0, 0))
             if k == 5:
-                dsts.append((dw, f, 5 * f, 4 * f, 5 * f, 3, 0, 0, sc, 0, 0))
+                dsts.append((dw, f, 5 * f, 4 * f, 5 * f, 3, f, 0, sc, 0, 0))
         # (bias gradients: accumulated by the conv launches that produced G's slots -- _rdb_backward / backward)
         ops.conv3x3_wgrad(A, G, roles, dsts)
 

@@ -300,7 +300,7 @@ def wgrad_workspace(device: torch.device) -> torch.Tensor:
 
 
 def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, roles, dsts) -> None:
-    """Tensor-core weight gradient.  roles: [(tap_begin, tap_count, x_c0, x_boxes, y_c0, n)];
+    """Tensor-core weight gradient.  roles: [(tap_begin, tap_count, x_c0, x_boxes, y_c0, n[, mode])];
     dsts: [(dw, o_count, i_total, i_begin, i_end, role, lane0, col0, scale, accumulate, perm)]."""
     _nhwc(x, "wgrad x")
     _nhwc(dy, "wgrad dy")
@@ -311,7 +311,8 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, roles, dsts) -> None:
     p.batch, p.height, p.width = x.shape[0], x.shape[1], x.shape[2]
     p.nroles = len(roles)
     for dst, r in zip(p.roles, roles):
-        dst.tap_begin, dst.tap_count, dst.x_c0, dst.x_boxes, dst.y_c0, dst.n = r
+        dst.tap_begin, dst.tap_count, dst.x_c0, dst.x_boxes, dst.y_c0, dst.n = r[:6]
+        dst.mode = r[6] if len(r) > 6 else 0
     p.ndst = len(dsts)
     for dst, d in zip(p.dst, dsts):
         dw = d[0]
