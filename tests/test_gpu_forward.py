@@ -63,6 +63,41 @@ def test_conv3x3_matches_torch_conv2d(dev, cin, in_coff, in_ctot, kc, cout):
     assert torch.all(out[..., :32] == 3.0)  # channels outside the window untouched
 
 
+@pytest.mark.parametrize("cin,h", [(96, 8 * 600 + 5), (160, 8 * 592)])
+def test_conv3x3_cta_pairs_bit_identical_to_single_ctas(dev, cin, h):
+    """Problems with >= 4 strips per SM can run as tcgen05 cta_group::2 pairs (weights split between the two CTAs;
+    opt-in: tap_mode 6 / XMM_DX_PAIR=1).  601 strips on 148 CTAs: some pairs have a peer with one strip fewer (dummy
+    strip); 592: none."""
+    from xmm_superres_denoise_b200 import ops
+    from xmm_superres_denoise_b200.engine import WeightArena, _Blob, _Segment
+
+    g = torch.Generator().manual_seed(cin)
+    b, w, cout, kc = 1, 40, 32, 32  # 3 tiles per strip, the last one ragged
+    x = torch.randn(b, h, w, 160, generator=g).to(torch.bfloat16)
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+    bias = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(b, h, w, cout, generator=g).to(torch.bfloat16)
+    arena = WeightArena()
+    wd, bd = wgt.to(dev), bias.to(dev)
+    arena.add(_Blob("c", cout, kc, cin // kc, [_Segment(wd, cin, 0, 0, 0, 0, cin, 1.0)], bd))
+    arena.ensure(dev)
+    xd, rd = x.to(dev), res.to(dev)
+    outs = []
+    for tap_mode in (6, 5):  # CTA pairs / single CTAs
+        out = torch.full((b, h, w, 64), 3.0, dtype=torch.bfloat16, device=dev)
+        ops.conv3x3(xd, 0, cin, arena.ptr("c"), kc, cout, out, 32, lrelu=0.2, s0=0.2, r1=rd, r1_coff=0, s1=1.0,
+                    tap_mode=tap_mode)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    xin = x[..., :cin].float().permute(0, 3, 1, 2)
+    want = F.leaky_relu(F.conv2d(xin, wgt.to(torch.bfloat16).float(), bias, padding=1), 0.2) * 0.2 \
+        + res.float().permute(0, 3, 1, 2)
+    got = outs[0][..., 32:].float().permute(0, 3, 1, 2).cpu()
+    assert rel_l2(got, want) < 4e-3
+    assert torch.all(outs[0][..., :32] == 3.0)
+
+
 def test_conv3x3_rejects_bad_arguments(dev):
     from xmm_superres_denoise_b200 import ops
 

@@ -27,8 +27,8 @@
 
 using namespace xmm;
 
-template <int KC, int NT, bool DX>
-static void run(int B, int H, int W, int k, int stages_cap) {
+template <int KC, int NT, bool DX, bool PAIR = false>
+static void run(int B, int H, int W, int k, int stages_cap, int rr = 0) {
   using Cfg = typename std::conditional<DX, DxCfg<KC, NT>, ConvCfg<KC, NT, 0>>::type;
   const int tw = DX ? kDxTileW : kTileW, th = DX ? kDxTileH : kTileH;
   const int cin = k * 32, ctot = 160;
@@ -52,29 +52,45 @@ static void run(int B, int H, int W, int k, int stages_cap) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > stages_cap) stages = stages_cap;
   a.stages = stages;
+  a.strip_rr = rr;
   a.epi.lrelu_slope = 0.2f; a.epi.s0 = 1.f; a.epi.out = out_d; a.epi.out_ctot = ctot; a.epi.out_coff = (k % 5) * 32;
   long long* prof;
-  CK(cudaMalloc(&prof, 148 * 12 * sizeof(long long)));
+  CK(cudaMalloc(&prof, 148 * 16 * sizeof(long long)));
   CUtensorMap tmap;
   if (make_nhwc_tmap(&tmap, in_d, B, H, W, ctot, KC, DX ? kDxTileW : kTileW + 2, DX ? kDxPatchH : kHaloH, false) != 0) { printf("tmap failed\n"); exit(2); }
   a.prof = prof;
   CUtensorMap tmap_o = tmap;
   if (DX && make_nhwc_tmap(&tmap_o, out_d, B, H, W, ctot, NT / 2, kDxTileW, 2, false) != 0) { printf("tmap failed\n"); exit(2); }
-  if constexpr (DX) CK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  if constexpr (DX) CK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   else CK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, NT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   float ms = 0;
   for (int rep = 0; rep < 3; ++rep) {
-    CK(cudaMemset(prof, 0, 148 * 12 * sizeof(long long)));
+    CK(cudaMemset(prof, 0, 148 * 16 * sizeof(long long)));
     cudaEventRecord(e0);
-    if constexpr (DX) { DxSideMaps sm_; sm_.m[0] = sm_.m[1] = sm_.m[2] = tmap; conv3x3_dx_kernel<KC, NT><<<148, kDxThreads, Cfg::smem_bytes(a.w_bytes, stages)>>>(tmap, tmap_o, sm_, a); }
+    if constexpr (DX && !PAIR) { DxSideMaps sm_; sm_.m[0] = sm_.m[1] = sm_.m[2] = tmap; conv3x3_dx_kernel<KC, NT><<<148, kDxThreads, Cfg::smem_bytes(a.w_bytes, stages)>>>(tmap, tmap_o, sm_, a); }
+    if constexpr (DX && PAIR) {
+      DxSideMaps sm_; sm_.m[0] = sm_.m[1] = sm_.m[2] = tmap;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(148); cfg.blockDim = dim3(kDxThreads); cfg.dynamicSmemBytes = Cfg::smem_bytes(a.w_bytes, stages);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      if (rep == 0) {
+        int ncl = 0;
+        CK(cudaOccupancyMaxActiveClusters(&ncl, conv3x3_dx_kernel<KC, NT, true>, &cfg));
+        printf("   max active clusters of 2: %d\n", ncl);
+      }
+      CK(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<KC, NT, true>, tmap, tmap_o, sm_, a));
+    }
     if constexpr (!DX) conv3x3_tc_kernel<KC, NT, 0><<<148, kConvThreads, Cfg::smem_bytes(a.w_bytes, stages)>>>(tmap, tmap, a);
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1);
   }
-  std::vector<long long> h(148 * 12);
+  std::vector<long long> h(148 * 16);
   CK(cudaMemcpy(h.data(), prof, h.size() * 8, cudaMemcpyDeviceToHost));
   double s[8] = {0};
   for (int c = 0; c < 148; ++c) for (int i = 0; i < 8; ++i) s[i] += double(h[c * 8 + i]) / 148;
@@ -83,13 +99,26 @@ static void run(int B, int H, int W, int k, int stages_cap) {
   for (int c = 0; c < 148; ++c) { mn = std::min(mn, h[c * 8 + 3]); mx = std::max(mx, h[c * 8 + 3]); }
   printf("   whole CTA: %.0f cycles in %.0f ns -> SM clock %.3f GHz\n", s[6], s[7], s[6] / s[7]);
   printf("   mma-loop total cycles per CTA: min %lld  avg %.0f  max %lld  (kernel %.0f)\n", mn, s[3], mx, ms * 1e-3 * 1e9 * s[6] / s[7]);
-  printf("%s k=%d cin=%d stages=%d: %.3f ms (%.0f cyc/tile at the measured clock) | per tile: mma-loop %.0f  wait_full %.0f  wait_tempty %.0f | producer wait_empty %.0f | epi wait_tfull %.0f  epi busy %.0f\n",
-         DX ? "dx" : "tc", k, cin, stages, ms, ms * 1e-3 * 1e9 * (s[6] / s[7]) / tiles, s[3] / tiles, s[2] / tiles, s[1] / tiles, s[0] / tiles, s[4] / tiles, s[5] / tiles);
+  printf("%s%s k=%d cin=%d stages=%d: %.3f ms (%.0f cyc/tile at the measured clock) | per tile: mma-loop %.0f  wait_full %.0f  wait_tempty %.0f | producer wait_empty %.0f | epi wait_tfull %.0f  epi busy %.0f\n",
+         DX ? "dx" : "tc", PAIR ? "-pair" : (rr ? "-rr" : ""), k, cin, stages, ms, ms * 1e-3 * 1e9 * (s[6] / s[7]) / tiles, s[3] / tiles, s[2] / tiles, s[1] / tiles, s[0] / tiles, s[4] / tiles, s[5] / tiles);
+  if (DX) {
+    double e[8] = {0};
+    for (int c = 0; c < 148; ++c) for (int i = 0; i < 8; ++i) e[i] += double(h[(148 + c) * 8 + i]) / 148;
+    printf("   epilogue phases per tile (warp 2): wait staging %.0f | tmem ld + release %.0f | mailbox/shuffle/sum %.0f | math + st.shared %.0f | fence + TMA store %.0f\n",
+           e[0] / tiles, e[1] / tiles, e[2] / tiles, e[3] / tiles, e[4] / tiles);
+  }
   cudaFree(in_d); cudaFree(out_d); cudaFree(blob); cudaFree(prof);
 }
 
 int main(int argc, char** argv) {
   const int cap = argc > 1 ? atoi(argv[1]) : 8;
+  if (argc > 2) {  // CTA pairs against single CTAs, both with round-robin strips
+    for (int k = 2; k <= 5; ++k) {
+      run<32, 32, true>(16, 416, 416, k, cap, 1);
+      run<32, 32, true, true>(16, 416, 416, k, cap, 1);
+    }
+    return 0;
+  }
   for (int k = 1; k <= 5; ++k) run<32, 32, true>(16, 416, 416, k, cap);
   for (int k = 1; k <= 5; ++k) run<32, 32, false>(16, 416, 416, k, cap);
   return 0;

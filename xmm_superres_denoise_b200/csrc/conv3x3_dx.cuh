@@ -38,6 +38,17 @@
 // by the tensor map), so the epilogue warps never synchronise with each other.  A TMA store may not start at a
 // negative coordinate (illegal instruction on B200), so tile 0 of a strip stores directly.
 //
+// CTA pairs (template PAIR, round-robin mode only).  An N = 96 MMA reads 4 KB of A + 3 KB of B from shared memory:
+// 56 cycles at 128 B/clk for 48 cycles of math -- and the TMA fills and the epilogue use the same port.  Two CTAs
+// of a cluster run as a tcgen05 cta_group::2 pair: each walks its OWN strips exactly as above (own activation
+// stages, TMEM accumulators, epilogue, stores), but the leader's MMA warp issues ONE M = 256 instruction for both
+// (rows 0..127 = the leader's pixel block, 128..255 = the peer's) and each CTA supplies only HALF of the weight
+// rows: 5.5 KB per CTA and instruction, 49 cycles measured (tools/probe_pair.cu).  The peer's resident weight image
+// is loaded 48 rows "early" so that the same descriptor offsets address rows 48..95 of every (chunk, filter row)
+// group.  The pair runs in lock step: the peer's TMA loads complete on the LEADER's full barriers, the peer's
+// epilogue warps release accumulators on the leader's barriers, the leader's commits are multicast to both CTAs.
+// When the peer has one strip fewer it repeats its first strip with all outputs suppressed.
+//
 // Everything else -- resident weights, TMA pipeline, TMEM accumulator ring, fused bias / LeakyReLU / mask /
 // residual / inverse-pixel-shuffle arithmetic -- is conv3x3_tc.cuh's.  The packed weight image is the same one
 // ([chunk][tap][Cout][KC]: the three dx taps of a row are adjacent, so they are one N = 3*Cout operand).
@@ -137,16 +148,20 @@ struct DxTile {
 };
 
 // The MMAs of one K-chunk (KC channels) of one tile: per filter row dy, KC/16 instructions of N = 3*NT.
-template <int KC, int NT>
+template <int KC, int NT, bool PAIR = false>
 __device__ __forceinline__ void dx_issue_chunk(uint32_t d_addr, uint64_t adesc_st, uint64_t bdesc_ch, bool first_chunk) {
   using Cfg = DxCfg<KC, NT>;
+  constexpr uint32_t kIdescPair = ptx::umma_idesc_bf16_f32(256, 3 * NT, 0, 0);
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
     for (int ks = 0; ks < Cfg::kKSteps; ++ks) {
       const uint64_t adesc = adesc_st + uint64_t((uint32_t(dy * kDxTileW * Cfg::kRowB) + uint32_t(ks * 32)) >> 4);
       const uint64_t bdesc = bdesc_ch + uint64_t((uint32_t(dy * 3 * Cfg::kTapBytes) + uint32_t(ks * 32)) >> 4);
-      ptx::umma_ss(d_addr, adesc, bdesc, Cfg::kIdesc, (first_chunk && dy == 0 && ks == 0) ? 0u : 1u);
+      if (PAIR)
+        ptx::umma_ss_pair(d_addr, adesc, bdesc, kIdescPair, (first_chunk && dy == 0 && ks == 0) ? 0u : 1u);
+      else
+        ptx::umma_ss(d_addr, adesc, bdesc, Cfg::kIdesc, (first_chunk && dy == 0 && ks == 0) ? 0u : 1u);
     }
   }
 }
@@ -163,6 +178,9 @@ struct DxEpiWarp {
   float bias[Cfg::kWarpCols];
   float csum[Cfg::kWarpCols];  // fused bias gradient: this lane's running column sums (ConvEpilogue::colsum)
   int par;             // tile parity (mailbox / staging double buffering)
+#ifdef XMM_CONV_PROFILE
+  long long phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   __device__ __forceinline__ void init(int warp, int lane_, const float* bias_s, uint8_t* out_s, uint8_t* mail_s) {
     lane = lane_;
     q = warp & 3;
@@ -198,7 +216,8 @@ struct DxEpiWarp {
 //   tx          tile column inside the strip (0: no left neighbour; the mailbox is not read)
 //   pre         pre-tile: only the carry is produced
 //   has_pend    lane 15 holds an unfinished column from the previous tile of this CTA
-template <int KC, int NT>
+//   PAIR        `tempty` is the LEADER CTA's barrier: released through its shared::cluster address
+template <int KC, int NT, bool PAIR = false>
 __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const ConvEpilogue& epi,
                                                  const CUtensorMap* tmap_out, uint32_t t_addr, uint64_t* tempty, int b,
                                                  int ty, int tx, int tiles_x, bool pre, bool has_pend, bool direct, int H,
@@ -210,10 +229,12 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
   const bool strip_end = (tx == tiles_x - 1) && !pre;
   const bool use_tma = !direct && !pre && tx > 0;
   uint8_t* stage = w.out_tile + w.par * Cfg::kWarpOutBytes;
+  XMM_EPI_T0();
   if (use_tma) {  // the TMA store issued two tiles ago has finished reading this staging tile
     if (ptx::elect_one()) ptx::bulk_wait_read<1>();
     __syncwarp();
   }
+  XMM_EPI_ADD(w, 0);
 #pragma unroll
   for (int cc = 0; cc < Cfg::kWarpChunks; ++cc) {
     uint32_t d0[16], d1[16], d2[16];
@@ -225,8 +246,14 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
     if (cc == Cfg::kWarpChunks - 1) {
       ptx::tc_fence_before();
       __syncwarp();
-      if (w.lane == 0) ptx::mbar_arrive(tempty);
+      if (w.lane == 0) {
+        if (PAIR)
+          ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(tempty), 0));
+        else
+          ptx::mbar_arrive(tempty);
+      }
     }
+    XMM_EPI_ADD(w, 1);
     const uint32_t a_w = w.slot(w.par, 0) + uint32_t(cc * 64), a_r = w.slot(w.par ^ 1, 0) + uint32_t(cc * 64);
     const uint32_t b_w = w.slot(w.par, 1) + uint32_t(cc * 64), b_r = w.slot(w.par ^ 1, 1) + uint32_t(cc * 64);
     // lane 15 publishes D_0[15] for the next tile's lane 0
@@ -264,6 +291,7 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
     for (int j = 0; j < 4; ++j) lds4_if(w.last_col, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], b_r + uint32_t(j * 16));
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += right[i];
+    XMM_EPI_ADD(w, 2);
     const int col = w.col_w + cc * 16;
     if (valid) {
       if (use_tma) {
@@ -287,6 +315,7 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
         conv_epilogue_cols<NT, 16>(epi, nullptr, v, col, b, y, x, H, W, epi.colsum != nullptr ? &w.csum[cc * 16] : nullptr);
       }
     }
+    XMM_EPI_ADD(w, 3);
     // End of the strip: column 15 of the last tile has no right neighbour (D_2[W] = 0).
     if (strip_end && w.last_col && y < H && tx * kDxTileW + 15 < W) {
       float f[16];
@@ -307,6 +336,7 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
       ptx::bulk_commit();
     }
   }
+  XMM_EPI_ADD(w, 4);
   w.par ^= 1;
 }
 
@@ -315,7 +345,7 @@ struct DxSideMaps {
   CUtensorMap m[3];
 };
 
-template <int KC, int NT>
+template <int KC, int NT, bool PAIR = false>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                   const __grid_constant__ DxSideMaps side_maps, const ConvArgs args) {
@@ -349,6 +379,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_g0_));
 #endif
 
+  const uint32_t pair_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = pair_rank == 0;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_in);
     ptx::prefetch_tmap(&tmap_out);
@@ -358,7 +390,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
     for (int a = 0; a < Cfg::kAccStages; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], kDxEpiWarps);
+      ptx::mbar_init(&tempty_bar[a], PAIR ? 2 * kDxEpiWarps : kDxEpiWarps);
     }
     ptx::mbar_init(w_bar, 1);
     for (int a = 0; a < 2; ++a) {
@@ -367,9 +399,17 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  if (warp == 1) {
+    if (PAIR)
+      ptx::tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_s);
+    else
+      ptx::tmem_alloc<Cfg::kTmemCols>(tmem_ptr_s);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    ptx::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+  else
+    __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -383,22 +423,41 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   const int g0 = (!rr && t0 % args.tiles_x != 0) ? t0 - 1 : t0;
   const int run_len = rr ? args.tiles_x : (t1 - g0);                 // tiles per run
   const int run_step = rr ? int(gridDim.x) * args.tiles_x : (t1 - g0 > 0 ? t1 - g0 : 1);  // distance between runs
+  // Number of runs.  A pair runs in lock step: both CTAs take the leader's count (>= the peer's); a run past this
+  // CTA's last strip is a dummy (its first strip again, nothing stored).
+  const int lead_g0 = PAIR ? int(blockIdx.x & ~1u) * args.tiles_x : g0;
+  const int nruns = t1 > lead_g0 ? (t1 - lead_g0 + run_step - 1) / run_step : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      const uint32_t wtot = args.w_bytes + Cfg::kBiasBytes;
-      ptx::mbar_expect_tx(w_bar, wtot);
       const uint8_t* gsrc = static_cast<const uint8_t*>(args.wblob);
-      for (uint32_t off = 0; off < wtot; off += 32768u) {
-        const uint32_t n = (wtot - off < 32768u) ? (wtot - off) : 32768u;
-        ptx::bulk_load(w_s + off, gsrc + off, n, w_bar);
+      if (PAIR && !leader) {
+        // the peer supplies rows [3*NT/2, 3*NT) of every (chunk, filter row) group: load the image half a group early
+        constexpr uint32_t kShift = uint32_t(3 * NT / 2) * Cfg::kRowB;
+        const uint32_t wpart = args.w_bytes - kShift;
+        ptx::mbar_expect_tx(w_bar, wpart + Cfg::kBiasBytes);
+        for (uint32_t off = 0; off < wpart; off += 32768u) {
+          const uint32_t n = (wpart - off < 32768u) ? (wpart - off) : 32768u;
+          ptx::bulk_load(w_s + off, gsrc + kShift + off, n, w_bar);
+        }
+        ptx::bulk_load(w_s + args.w_bytes, gsrc + args.w_bytes, Cfg::kBiasBytes, w_bar);
+        ptx::mbar_wait(w_bar, 0);  // the leader's MMAs read these weights once this CTA's first stage has landed
+      } else {
+        const uint32_t wtot = args.w_bytes + Cfg::kBiasBytes;
+        ptx::mbar_expect_tx(w_bar, wtot);
+        for (uint32_t off = 0; off < wtot; off += 32768u) {
+          const uint32_t n = (wtot - off < 32768u) ? (wtot - off) : 32768u;
+          ptx::bulk_load(w_s + off, gsrc + off, n, w_bar);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
       int sbuf = 0;
       uint32_t sphase = 0;
-      for (int r0 = g0; r0 < t1; r0 += run_step) {
+      for (int run = 0; run < nruns; ++run) {
+        const bool dummy = g0 + run * run_step >= t1;
+        const int r0 = dummy ? g0 : g0 + run * run_step;
         DxTile t(r0, args.tiles_x, args.tiles_y);
         for (int g = r0; g < r0 + run_len; ++g, t.next(args.tiles_x, args.tiles_y)) {
           const int y0 = t.ty * kDxTileH - 1, x0 = t.tx * kDxTileW;
@@ -406,15 +465,21 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             XMM_PROF_T0();
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             XMM_PROF_ADD(0);
-            ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            ptx::tma_load_4d(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in, &full_bar[stage],
-                             args.cin_off + ch * KC, x0, y0, t.b);
+            if (PAIR) {  // both CTAs' stages complete on the leader's barrier
+              if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              ptx::tma_load_4d_pair(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in,
+                                    ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0), args.cin_off + ch * KC, x0, y0, t.b);
+            } else {
+              ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              ptx::tma_load_4d(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in, &full_bar[stage],
+                               args.cin_off + ch * KC, x0, y0, t.b);
+            }
             if (++stage == args.stages) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          if (nside > 0 && g >= t0) {  // the output pixels' mask / residual tiles (not for pre-tiles)
+          if (nside > 0 && g >= t0 && !dummy) {  // the output pixels' mask / residual tiles (not for pre-tiles)
             ptx::mbar_wait(&sempty_bar[sbuf], sphase ^ 1u);
             ptx::mbar_expect_tx(&sfull_bar[sbuf], uint32_t(nside) * Cfg::kSideTileBytes);
             uint8_t* dst = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
@@ -437,7 +502,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (ptx::elect_one()) {
+    if (leader && ptx::elect_one()) {
       ptx::mbar_wait(w_bar, 0);
       ptx::tc_fence_after();
       const uint32_t w_addr = ptx::smem_u32(w_s);
@@ -449,8 +514,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       XMM_PROF_START(3);
-      int my_tiles = 0;
-      for (int r0 = g0; r0 < t1; r0 += run_step) my_tiles += run_len;
+      const int my_tiles = nruns * run_len;
       for (int g = 0; g < my_tiles; ++g) {
         XMM_PROF_T0();
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -464,14 +528,20 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           ptx::tc_fence_after();
           const uint64_t adesc_st = adesc0 + uint64_t((uint32_t(stage) * Cfg::kStageBytes) >> 4);
           const uint64_t bdesc_ch = bdesc0 + uint64_t((uint32_t(ch) * 9u * Cfg::kTapBytes) >> 4);
-          dx_issue_chunk<KC, NT>(d_addr, adesc_st, bdesc_ch, ch == 0);
-          ptx::umma_commit(&empty_bar[stage]);
+          dx_issue_chunk<KC, NT, PAIR>(d_addr, adesc_st, bdesc_ch, ch == 0);
+          if (PAIR)
+            ptx::umma_commit_pair(&empty_bar[stage]);
+          else
+            ptx::umma_commit(&empty_bar[stage]);
           if (++stage == args.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        ptx::umma_commit(&tfull_bar[acc]);
+        if (PAIR)
+          ptx::umma_commit_pair(&tfull_bar[acc]);
+        else
+          ptx::umma_commit(&tfull_bar[acc]);
         if (++acc == Cfg::kAccStages) {
           acc = 0;
           acc_phase ^= 1u;
@@ -490,7 +560,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     uint32_t acc_phase = 0;
     int sbuf = 0;
     uint32_t sphase = 0;
-    for (int r0 = g0; r0 < t1; r0 += run_step) {
+    for (int run = 0; run < nruns; ++run) {
+      const bool dummy = g0 + run * run_step >= t1;
+      const int r0 = dummy ? g0 : g0 + run * run_step;
       DxTile t(r0, args.tiles_x, args.tiles_y);  // advanced incrementally: no divisions in the tile loop
       for (int g = r0; g < r0 + run_len; ++g) {
         XMM_PROF_T0();
@@ -499,7 +571,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         XMM_PROF_T0();
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(w.q * 32) << 16) + uint32_t(acc * Cfg::kAccCols);
-        const bool sides = nside > 0 && g >= t0;
+        const bool sides = nside > 0 && g >= t0 && !dummy;
         const uint8_t* side_tiles[3] = {nullptr, nullptr, nullptr};
         if (sides) {
           ptx::mbar_wait(&sfull_bar[sbuf], sphase);
@@ -512,9 +584,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
               src += Cfg::kSideTileBytes;
             }
         }
-        dx_epilogue_tile<KC, NT>(w, args.epi, &tmap_out, t_addr, &tempty_bar[acc], t.b, t.ty, t.tx, args.tiles_x,
-                                 /*pre=*/g < t0, /*has_pend=*/(t.tx > 0) && (g != r0), direct, args.height, args.width,
-                                 sides ? side_tiles : nullptr);
+        dx_epilogue_tile<KC, NT, PAIR>(w, args.epi, &tmap_out, t_addr, &tempty_bar[acc], t.b, t.ty, t.tx, args.tiles_x,
+                                       /*pre=*/g < t0 || dummy, /*has_pend=*/(t.tx > 0) && (g != r0) && !dummy, direct,
+                                       args.height, args.width, sides ? side_tiles : nullptr);
         if (sides) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&sempty_bar[sbuf]);
@@ -534,13 +606,23 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     if (ptx::elect_one()) ptx::bulk_wait<0>();  // this warp's stores complete before the CTA (and its smem) goes away
     if (args.epi.colsum != nullptr) colsum_flush<Cfg::kWarpCols>(args.epi, w.csum, w.col_w, lane);
     if (warp == 2 && lane == 0) { XMM_PROF_FLUSH(4); XMM_PROF_FLUSH(5); }
+#ifdef XMM_CONV_PROFILE
+    if (warp == 2 && lane == 0)
+      for (int i = 0; i < 8; ++i) args.prof[size_t(148 + blockIdx.x) * 8 + i] = w.phase[i];
+#endif
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    ptx::cluster_sync();  // neither CTA's shared memory / TMEM may go away while the other still uses it
+  else
+    __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR)
+      ptx::tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else
+      ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 #ifdef XMM_CONV_PROFILE
   if (threadIdx.x == 0) {

@@ -28,7 +28,12 @@
 #define XMM_PROF_START(i) long long prof_s_ = clock64()
 #define XMM_PROF_STOP(i) prof_acc_[i] += clock64() - prof_s_
 #define XMM_PROF_FLUSH(i) args.prof[size_t(blockIdx.x) * 8 + (i)] = prof_acc_[i]
+// finer phases inside the column-scatter epilogue (one warp reports): slots [148*8 + cta*8 + i]
+#define XMM_EPI_T0() long long epi_t_ = clock64()
+#define XMM_EPI_ADD(w, i) { const long long n_ = clock64(); (w).phase[i] += n_ - epi_t_; epi_t_ = n_; }
 #else
+#define XMM_EPI_T0()
+#define XMM_EPI_ADD(w, i)
 #define XMM_PROF_T0()
 #define XMM_PROF_ADD(i)
 #define XMM_PROF_START(i)

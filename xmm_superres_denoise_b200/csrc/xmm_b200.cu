@@ -222,6 +222,33 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   const long long nstrips = (long long)a.tiles_y * p.batch;
   // (cin <= 64 is not DRAM-bound: there the round-robin's wave quantisation only pays off with many strips)
   a.strip_rr = rr_env >= 0 ? (rr_env != 0) : (nstrips >= 4LL * grid && (a.nchunks >= 3 || nstrips >= 16LL * grid));
+  // Round-robin strips on an even grid: CTA pairs (cta_group::2, the weight operand split between the two SMs of a
+  // TPC).  Opt-in (XMM_DX_PAIR=1): bit-identical and the MMA stream gets cheaper (49 vs 56 cycles), but the layers are
+  // epilogue- (cin <= 96) or HBM-bound (cin >= 128), so the launch is not faster (profiles/r01_conv_prof_pair.log).
+  static const int pair_env = [] { const char* e = getenv("XMM_DX_PAIR"); return e ? atoi(e) : 0; }();
+  if (KC == 32 && NT == 32 && (pair_env || p.tap_mode == 6) && p.tap_mode != 5 && a.strip_rr && grid % 2 == 0 &&
+      nstrips >= grid) {
+    static bool pair_attr_set = false;
+    if (!pair_attr_set) {
+      XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       dev.max_smem_optin));
+      pair_attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(kDxThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XMM_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<KC, NT, true>, tmap, tmap_out, sides, a));
+    return XMM_OK;
+  }
   conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, sides, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
@@ -282,7 +309,7 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   const bool dx_auto = p.tap_mode <= 0 && p.kc == 32 && p.cout == 32 && p.cin >= 64 &&
                        DxCfg<32, 32>::smem_bytes(uint32_t(p.cin / 32) * 9u * DxCfg<32, 32>::kTapBytes, 4) <=
                            size_t(dev.max_smem_optin);  // >= 4 pipeline stages next to the resident weights
-  if (p.tap_mode == 4 || dx_auto) {
+  if (p.tap_mode == 4 || p.tap_mode == 5 || p.tap_mode == 6 || dx_auto) {  // 5 / 6: without / with CTA pairs
     if (p.kc == 32 && p.cout == 32) return launch_conv_dx<32, 32>(p, dev, s);
     if (p.kc == 64 && p.cout == 64) return launch_conv_dx<64, 64>(p, dev, s);
     return fail(XMM_ERR_INVALID_ARGUMENT, "conv3x3: the column-scatter form is built for cout = kc = 32 or 64");
