@@ -89,6 +89,38 @@ def test_full_gradient_vector_vs_oracle(dev, kind):
     assert not bad, bad
 
 
+def test_sr_4x_gradients_vs_oracle(dev):
+    """GeneratorRRDB_SR with num_upsample=2 (the class default; generator_rrdb.py:72-101): backward through two
+    conv -> LeakyReLU(0.01) -> PixelShuffle stages, output and every parameter gradient against the oracle."""
+    from xmm_superres_denoise_b200.models import GeneratorRRDB_SR
+
+    nf, nb = 32, 1
+    sd = O.init_state_dict("sr", 1, 1, nf, nb, 2, seed=21)  # (a seed whose random-init output is not clamped to 0)
+    lr, hr, t_lr, t_hr = count_batch(2, seed=5, kind="sr")
+    x = O.normalize_image(torch.from_numpy(lr[:, :, 160:208, 168:208].astype(np.float32) / t_lr), LR_MAX, "sqrt")
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    want_out = O.model_forward(x, sdg, "sr", 2)
+    assert want_out.shape[-2:] == (192, 160)
+    target = (want_out.detach() * 0.7 + 0.05).clamp(0, 1)
+    ((want_out - target).abs().mean() + ((want_out - target) ** 2).mean()).backward()
+    m = GeneratorRRDB_SR(1, 1, nf, nb, num_upsample=2)
+    m.load_state_dict(sd)
+    m = m.to(dev).train()
+    out = torch.clamp(m(x.to(dev)), 0, 1)
+    assert rel_l2(out.detach().cpu(), want_out.detach()) < REL_L2_BF16
+    t = target.to(dev)
+    ((out - t).abs().mean() + ((out - t) ** 2).mean()).backward()
+    got = torch.cat([p.grad.reshape(-1) for _, p in m.named_parameters()]).cpu()
+    want = torch.cat([sdg[n].grad.reshape(-1) for n, _ in m.named_parameters()])
+    r = rel_l2(got, want)
+    print(f"sr 4x: full gradient rel-L2 = {r:.3e}")
+    assert r < GRAD_REL
+    per = {n: rel_l2(p.grad.cpu(), sdg[n].grad) for n, p in m.named_parameters() if sdg[n].grad.norm() > 0}
+    bad = {n: v for n, v in per.items() if v > 5 * GRAD_REL}
+    assert not bad, bad
+
+
 def test_adam_training_trajectory_matches_oracle(dev):
     """Four Adam steps (lr 1e-4, betas (0.9, 0.999): res/configs/models.toml:7-8, models/model.py:239-247)
     on the CUDA path and on the oracle (CPU autograd): per-step losses agree and the packed weights

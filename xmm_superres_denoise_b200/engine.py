@@ -10,6 +10,8 @@ Owns what the reference leaves to autograd and cuDNN:
 """
 from __future__ import annotations
 
+import gc
+
 import ctypes
 import os
 from dataclasses import dataclass, field
@@ -333,6 +335,7 @@ class RRDBEngine(_LayerPlans):
             with torch.cuda.stream(side):  # first-call setup (function attributes, TMA descriptors) outside the capture
                 self._forward_inference_eager(static_in)
             torch.cuda.current_stream(x.device).wait_stream(side)
+            gc.collect()  # a collected engine / graph releasing device memory in mid-capture would invalidate the capture
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = self._forward_inference_eager(static_in)

@@ -237,8 +237,6 @@ class TrainEngine(RRDBEngine):
                             mask_slope=0.01, pixel_shuffle=2)
                 dy, blob, nin = bufs[f"d_up{s}"], f"d.up{s}", 4 * f
                 self._single_conv_wgrad(g.upsampling[3 * s], ups[s], dy, grads, perm=1)
-                if s > 0:
-                    raise NotImplementedError("backward through more than one upsampling stage is not built yet")
             ops.conv3x3(dy, 0, nin, a.ptr(blob), kc, f, bufs["d_trunk"], 0)
         d_trunk = bufs["d_trunk"]  # dL/d(fea + trunk_conv(...)): feeds trunk_conv and the `fea` skip
         last_act = bufs["act"][3 * self.nb]
