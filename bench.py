@@ -269,7 +269,7 @@ def bench_train(args, kind: str, dev, dist, rank: int, world: int, local_rank: i
     ach = flop * args.steps / (ms * 1e-3) / 1e12
     name = ("configs[2]: XMM-DeNoise RRDB training, L1+Poisson" if kind == "dn"
             else "configs[3]: XMM-SuperRes 2x RRDB training, L1+Poisson+MS-SSIM")
-    res = {"metric": f"RRDB {'DN' if kind == 'dn' else 'SR-2x'} training images/sec (F=32, nb=4, batch {B}/GPU)",
+    res = {"metric": f"RRDB {'DN' if kind == 'dn' else 'SR-2x'} training images/sec (F={NF}, nb={NB}, batch {B}/GPU)",
            "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -289,6 +289,7 @@ def bench_train(args, kind: str, dev, dist, rank: int, world: int, local_rank: i
 
 
 def main() -> None:
+    global NF, NB
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -299,7 +300,10 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64 inference / 16 training)")
     ap.add_argument("--no-train-extra", action="store_true", help="skip the short training measurements in `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--filters", type=int, default=NF, help="developer sweeps only (BASELINE's configs are 32 / 4)")
+    ap.add_argument("--blocks", type=int, default=NB)
     args = ap.parse_args()
+    NF, NB = args.filters, args.blocks
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
 

@@ -105,6 +105,9 @@ typedef struct {
   float* colsum;      /* optional (cout == 32): colsum[n] += colsum_scale * sum over all pixels of the value written
                          to channel n -- the bias gradient whose integrand this data-gradient layer produces       */
   float colsum_scale;
+  int shuffle_stride; /* pixel_shuffle == 2 only: channel distance between the four (y&1, x&1) blocks of the output
+                         (0 = cout).  A layer split along its output channels writes part n0 with out_coff + n0 and
+                         the full layer's cout here.                                                              */
 } xmm_conv3x3_params;
 
 int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);
@@ -236,6 +239,8 @@ typedef struct {
   float scale;
   int accumulate;           /* 0: overwrite dw, 1: add                                          */
   int perm;                 /* 1: columns are in PixelShuffle-packed order                      */
+  int o_begin, o_total;     /* the role covers output channels [o_begin, o_begin + o_count) of o_total
+                               (o_total 0 = o_count, o_begin 0): layers with more output channels than lanes */
 } xmm_wgrad_dst;
 
 typedef struct {

@@ -173,6 +173,9 @@ def test_run_inference_on_fits_files(dev, tmp_path, golden_dir, kind):
     cfg = {"lr_res": 416, "hr_res": 832 if kind == "sr" else 416, "dataset_lr_res": 416, "data_scaling": "sqrt",
            "lr_max": LR_MAX, "hr_max": HR_MAX if kind == "sr" else LR_MAX, "hr_exp": 100 if kind == "sr" else 50,
            "det_mask": True}
+    # random init: seeds whose output on this image is not clamped to zero (most are: the comparison would then rest on
+    # a handful of pixels)
+    torch.manual_seed(3 if kind == "dn" else 1)
     with pytest.warns(UserWarning, match="randomly initialised"):
         gen = build_generator(cfg, {"filters": 32, "residual_blocks": 1}, None, dev)
     sd = {k: v.detach().cpu() for k, v in gen.state_dict().items()}

@@ -121,6 +121,39 @@ def test_sr_4x_gradients_vs_oracle(dev):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("kind", ["dn", "sr"])
+def test_64_filter_gradients_vs_oracle(dev, kind):
+    """num_filters=64 (the ESRGAN width of BASELINE's sweep): data-gradient layers split along their output channels,
+    five weight-gradient launches per dense block, bias gradients by a column-sum pass -- output and the whole
+    gradient vector against the oracle's autograd."""
+    nf, nb = 64, 1
+    sd = O.init_state_dict(kind, 1, 1, nf, nb, 1, seed=25)  # (a seed whose random-init output is not clamped away)
+    lr, hr, t_lr, t_hr = count_batch(2, seed=5, kind=kind)
+    x = O.normalize_image(torch.from_numpy(lr[:, :, 160:208, 168:208].astype(np.float32) / t_lr), LR_MAX, "sqrt")
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    want_out = O.model_forward(x, sdg, kind, 1)
+    target = (want_out.detach() * 0.7 + 0.05).clamp(0, 1)
+    ((want_out - target).abs().mean() + ((want_out - target) ** 2).mean()).backward()
+    m = _model(kind, nf, nb, sd, dev)
+    out = torch.clamp(m(x.to(dev)), 0, 1)
+    r_out = rel_l2(out.detach().cpu(), want_out.detach())
+    t = target.to(dev)
+    ((out - t).abs().mean() + ((out - t) ** 2).mean()).backward()
+    got = torch.cat([p.grad.reshape(-1) for _, p in m.named_parameters()]).cpu()
+    want = torch.cat([sdg[n].grad.reshape(-1) for n, _ in m.named_parameters()])
+    r = rel_l2(got, want)
+    per = {n: rel_l2(p.grad.cpu(), sdg[n].grad) for n, p in m.named_parameters() if sdg[n].grad.norm() > 0}
+    print(f"{kind} F=64: output rel-L2 = {r_out:.3e}, full gradient rel-L2 = {r:.3e}, worst tensor "
+          f"{max(per, key=per.get)} = {max(per.values()):.3e}")
+    assert r_out < REL_L2_BF16
+    assert r < GRAD_REL
+    # conv_first.weight (576 numbers) is x correlated with the SUM of two bf16-stored gradient maps that largely cancel
+    # at nb = 1 -- the same conditioning as dL/dx in test_gradients_match_reference_golden; held to 1e-1
+    bad = {n: v for n, v in per.items() if v > (1e-1 if n == "conv_first.weight" else 5 * GRAD_REL)}
+    assert not bad, bad
+
+
 def test_adam_training_trajectory_matches_oracle(dev):
     """Four Adam steps (lr 1e-4, betas (0.9, 0.999): res/configs/models.toml:7-8, models/model.py:239-247)
     on the CUDA path and on the oracle (CPU autograd): per-step losses agree and the packed weights

@@ -36,7 +36,8 @@ class Conv3x3Params(Structure):
                 ("r1", c_void_p), ("r1_ctot", c_int), ("r1_coff", c_int), ("s1", c_float),
                 ("r2", c_void_p), ("r2_ctot", c_int), ("r2_coff", c_int), ("s2", c_float),
                 ("out", c_void_p), ("out_ctot", c_int), ("out_coff", c_int),
-                ("pixel_shuffle", c_int), ("tap_mode", c_int), ("colsum", c_void_p), ("colsum_scale", c_float)]
+                ("pixel_shuffle", c_int), ("tap_mode", c_int), ("colsum", c_void_p), ("colsum_scale", c_float),
+                ("shuffle_stride", c_int)]
 
 
 class NormalizeParams(Structure):
@@ -70,7 +71,7 @@ class WgradRole(Structure):
 class WgradDst(Structure):
     _fields_ = [("dw", c_void_p), ("o_count", c_int), ("i_total", c_int), ("i_begin", c_int), ("i_end", c_int),
                 ("role", c_int), ("lane0", c_int), ("col0", c_int), ("scale", c_float), ("accumulate", c_int),
-                ("perm", c_int)]
+                ("perm", c_int), ("o_begin", c_int), ("o_total", c_int)]
 
 
 class WgradParams(Structure):

@@ -74,6 +74,7 @@ struct ConvEpilogue {
   // 1: PixelShuffle(2) store: out is [B][2H][2W][out_ctot]; column group g=(i,j) -> pixel (2y+i,2x+j)
   // 2: inverse (backward of 1): out is [B][H/2][W/2][out_ctot]; pixel (y,x) -> (y/2,x/2), channel block g=(y&1,x&1)
   int pixel_shuffle;
+  int shuffle_stride;  // mode 2: channel distance between the four (y&1, x&1) blocks (the full layer's cout)
   // Image mode (conv_last, generator_rrdb.py:48-54,107-108,132-135, on the tensor cores): img_out != nullptr.
   // The packed layer holds bf16(w) in rows [0, img_cout) and the low-order halves bf16(w - bf16(w)) in rows
   // [16, 16 + img_cout); out[b][o][y][x] = clamp?(acc[o] + acc[16+o] + bias[o] + img_res[...]) in fp32 NCHW.
@@ -231,7 +232,7 @@ __device__ __forceinline__ void conv_epilogue_cols(const ConvEpilogue& e, const 
   if (e.pixel_shuffle == 2) {
     const int g = ((y & 1) << 1) | (x & 1);
     const size_t lp = (size_t(b) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
-    op = reinterpret_cast<uint4*>(e.out + lp * e.out_ctot + e.out_coff + g * NT + col0);
+    op = reinterpret_cast<uint4*>(e.out + lp * e.out_ctot + e.out_coff + g * e.shuffle_stride + col0);
   } else if (e.pixel_shuffle == 1) {
     constexpr int kGroup = NT / 4;  // channels of the shuffled (HR) tensor
     const int g = col0 / kGroup, c = col0 % kGroup;

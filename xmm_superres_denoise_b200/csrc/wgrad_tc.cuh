@@ -233,6 +233,7 @@ struct WgradDst {
   float scale;
   int accumulate;       // 0: overwrite, 1: add to the existing gradient
   int perm;             // 1: output channel o is the PixelShuffle-packed index (see shuffle_perm)
+  int o_begin, o_total; // this destination covers output channels [o_begin, o_begin + o_count) of o_total
 };
 
 struct WgradReduceArgs {
@@ -259,7 +260,7 @@ __global__ void wgrad_reduce_kernel(const WgradReduceArgs a, int num_tiles) {
                                       : size_t(d.lane0 + i) * 512 + size_t(t * role.n + d.col0 + o);
     float s = 0.f;
     for (int c = 0; c < active; ++c) s += a.ws[size_t(role.cta_begin + c) * kWgWsFloatsPerCta + off];
-    const int oo = d.perm ? shuffle_perm(o, d.o_count / 4) : o;
+    const int oo = d.perm ? shuffle_perm(d.o_begin + o, d.o_total / 4) : d.o_begin + o;
     float* p = d.dw + (size_t(oo) * d.i_total + (d.i_begin + i)) * 9 + (role.mode == 1 ? t : role.tap_begin + t);
     *p = d.accumulate ? (*p + d.scale * s) : d.scale * s;
   }

@@ -90,6 +90,7 @@ void fill_epilogue(ConvEpilogue& e, const xmm_conv3x3_params& p) {
   e.r2 = static_cast<const __nv_bfloat16*>(p.r2); e.r2_ctot = p.r2_ctot; e.r2_coff = p.r2_coff;
   e.out = static_cast<__nv_bfloat16*>(p.out); e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
   e.pixel_shuffle = p.pixel_shuffle;
+  e.shuffle_stride = p.shuffle_stride > 0 ? p.shuffle_stride : p.cout;
   e.img_out = nullptr; e.img_res = nullptr; e.img_pre = nullptr; e.img_cout = 0; e.img_clamp = 0;
   e.colsum = p.colsum; e.colsum_scale = p.colsum_scale;
 }
@@ -275,7 +276,10 @@ int check_conv_params(const xmm_conv3x3_params& p) {
   XMM_REQUIRE(p.cin > 0 && p.cin % p.kc == 0, "conv3x3: cin=%d is not a multiple of kc=%d", p.cin, p.kc);
   XMM_REQUIRE(p.in_ctot % 8 == 0 && p.in_coff % 8 == 0 && p.in_coff + p.cin <= p.in_ctot,
               "conv3x3: input channel window [%d,%d) of %d", p.in_coff, p.in_coff + p.cin, p.in_ctot);
-  const int out_c = p.pixel_shuffle == 1 ? p.cout / 4 : (p.pixel_shuffle == 2 ? 4 * p.cout : p.cout);
+  XMM_REQUIRE(p.shuffle_stride == 0 || (p.pixel_shuffle == 2 && p.shuffle_stride >= p.cout && p.shuffle_stride % 8 == 0),
+              "conv3x3: shuffle_stride is the inverse pixel shuffle's block distance (>= cout)");
+  const int out_c = p.pixel_shuffle == 1 ? p.cout / 4
+                    : (p.pixel_shuffle == 2 ? 3 * (p.shuffle_stride > 0 ? p.shuffle_stride : p.cout) + p.cout : p.cout);
   XMM_REQUIRE(p.pixel_shuffle >= 0 && p.pixel_shuffle <= 2, "conv3x3: pixel_shuffle must be 0, 1 or 2");
   XMM_REQUIRE(p.pixel_shuffle != 2 || (p.height % 2 == 0 && p.width % 2 == 0 && !p.r1 && !p.r2),
               "conv3x3: inverse pixel shuffle needs even height/width and no residual");
@@ -807,6 +811,8 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
     WgradDst& d = ra.dst[i];
     d.dw = q.dw; d.o_count = q.o_count; d.i_total = q.i_total; d.i_begin = q.i_begin; d.i_end = q.i_end;
     d.role = q.role; d.lane0 = q.lane0; d.col0 = q.col0; d.scale = q.scale; d.accumulate = q.accumulate; d.perm = q.perm;
+    d.o_begin = q.o_begin; d.o_total = q.o_total > 0 ? q.o_total : q.o_count;
+    XMM_REQUIRE(q.o_begin >= 0 && q.o_begin + q.o_count <= d.o_total, "wgrad: destination %d output-channel window", i);
   }
 
   CUtensorMap tx, ty, tx32;

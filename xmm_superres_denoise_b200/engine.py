@@ -161,15 +161,38 @@ class _LayerPlans:
             plan.append((pname, 32, part, n0))
         self.plans[name] = plan
 
+    def _add_planned(self, name: str, rows: int, k_total: int, make_blob) -> None:
+        """A packed layer described by ``make_blob(blob_name, n0, nt, kc) -> _Blob`` (rows [n0, n0+nt) of the layer's
+        `rows` GEMM columns, K = k_total channels): one blob if its weights fit next to the pipeline stages, else
+        parts of 32 rows with 32-channel K chunks (data-gradient layers of the 64-filter generators)."""
+        if 9 * k_total * rows * 2 <= _WEIGHT_BUDGET:
+            self.arena.add(make_blob(name, 0, rows, self.kc))
+            self.plans[name] = [(name, self.kc, rows, 0)]
+            return
+        if rows % 32 or 9 * k_total * 32 * 2 > 190 * 1024:
+            raise NotImplementedError(f"{name}: a {k_total}->{rows} layer does not fit the resident-weight kernels")
+        plan = []
+        for n0 in range(0, rows, 32):
+            pname = f"{name}.n{n0}"
+            self.arena.add(make_blob(pname, n0, 32, 32))
+            plan.append((pname, 32, 32, n0))
+        self.plans[name] = plan
+
     def _conv(self, name: str, inp: torch.Tensor, in_coff: int, cin: int, out: torch.Tensor, out_coff: int, **kw):
         """The launches of one planned layer as (args, kwargs) for ops.conv3x3 / ops.conv3x3_chain."""
         calls = []
         shuffle = kw.get("pixel_shuffle", 0) == 1
-        for blob, kc, nt, n0 in self.plans[name]:
+        plan = self.plans[name]
+        rows = sum(nt for _, _, nt, _ in plan)
+        for blob, kc, nt, n0 in plan:
             k2 = dict(kw)
             for key in ("r1_coff", "r2_coff", "mask_coff"):
                 if key in k2 and k2.get(key[:-5]) is not None:
                     k2[key] = k2[key] + n0
+            if k2.get("colsum") is not None:  # fused bias gradient: this part's window of the bias gradient
+                k2["colsum"] = k2["colsum"][n0:n0 + nt]
+            if k2.get("pixel_shuffle", 0) == 2 and len(plan) > 1:
+                k2["shuffle_stride"] = rows  # the four (y&1, x&1) blocks are a full layer apart
             calls.append(((inp, in_coff, cin, self.arena.ptr(blob), kc, nt, out, out_coff + (n0 // 4 if shuffle else n0)),
                           k2))
         return calls

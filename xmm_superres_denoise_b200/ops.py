@@ -39,7 +39,7 @@ def _conv3x3_params(p: Conv3x3Params, inp: torch.Tensor, in_coff: int, cin: int,
                     r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
                     mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
                     pixel_shuffle: int = 0, tap_mode: int = 0, colsum: Optional[torch.Tensor] = None,
-                    colsum_scale: float = 1.0) -> None:
+                    colsum_scale: float = 1.0, shuffle_stride: int = 0) -> None:
     _nhwc(inp, "conv3x3 input")
     _nhwc(out, "conv3x3 output")
     b, h, w, ctot = inp.shape
@@ -66,6 +66,7 @@ def _conv3x3_params(p: Conv3x3Params, inp: torch.Tensor, in_coff: int, cin: int,
         raise RuntimeError(f"conv3x3 output: expected spatial shape {exp}, got {tuple(out.shape[:3])}")
     p.out, p.out_ctot, p.out_coff = out.data_ptr(), out.shape[3], out_coff
     p.pixel_shuffle = pixel_shuffle
+    p.shuffle_stride = shuffle_stride
     p.tap_mode = tap_mode
     if colsum is not None:
         _lib.require_cuda_tensor(colsum, torch.float32, "conv3x3 colsum")
@@ -301,7 +302,7 @@ def wgrad_workspace(device: torch.device) -> torch.Tensor:
 
 def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, roles, dsts) -> None:
     """Tensor-core weight gradient.  roles: [(tap_begin, tap_count, x_c0, x_boxes, y_c0, n[, mode])];
-    dsts: [(dw, o_count, i_total, i_begin, i_end, role, lane0, col0, scale, accumulate, perm)]."""
+    dsts: [(dw, o_count, i_total, i_begin, i_end, role, lane0, col0, scale, accumulate, perm[, o_begin, o_total])]."""
     _nhwc(x, "wgrad x")
     _nhwc(dy, "wgrad dy")
     if x.shape[:3] != dy.shape[:3]:
@@ -318,7 +319,8 @@ def conv3x3_wgrad(x: torch.Tensor, dy: torch.Tensor, roles, dsts) -> None:
         dw = d[0]
         _lib.require_cuda_tensor(dw, torch.float32, "wgrad dw")
         (dst.o_count, dst.i_total, dst.i_begin, dst.i_end, dst.role, dst.lane0, dst.col0, dst.scale, dst.accumulate,
-         dst.perm) = d[1:]
+         dst.perm) = d[1:11]
+        dst.o_begin, dst.o_total = (d[11], d[12]) if len(d) > 11 else (0, 0)
         dst.dw = dw.data_ptr()
     p.workspace = wgrad_workspace(x.device).data_ptr()
     _lib.check(_lib.load().xmm_conv3x3_wgrad(ctypes.byref(p), _lib.stream_ptr()))
