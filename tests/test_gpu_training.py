@@ -223,3 +223,36 @@ def test_trainstep_matches_autograd_path_and_oracle_adam(dev, kind):
     p0 = torch.cat([sd[n].reshape(-1) for n, _ in a.named_parameters()]).to(dev)
     assert rel_l2(pb - p0, pa - p0) < 1e-3
     assert list(b.state_dict().keys()) == list(a.state_dict().keys())
+
+
+@pytest.mark.parametrize("kind,weights", [("dn", {"l1": 0.5, "poisson": 0.5}),
+                                          ("sr", {"l1": 0.3, "poisson": 0.3, "ms_ssim": 0.4})])
+def test_trainstep_cuda_graph_replay_matches_eager(dev, kind, weights):
+    """TrainStep(use_graph=True): the first step of a shape runs eagerly, the second captures forward + loss +
+    backward as one CUDA graph, later steps replay it.  Before every step the graph model is put into the eager
+    model's state (the fused bias-gradient sums use atomics and Adam's first steps amplify that rounding noise, so
+    two free-running trajectories -- eager or not -- drift apart); from equal states the step must give the same loss
+    and the same gradient."""
+    from xmm_superres_denoise_b200.training import TrainStep
+    from xmm_superres_denoise_b200.utils.loss_functions import create_loss
+
+    sd = O.init_state_dict(kind, 1, 1, 32, 1, 1, seed=25 if kind == "dn" else 15)
+    g = torch.Generator().manual_seed(1)
+    s = 1 if kind == "dn" else 2
+    h, w = (96, 80) if kind == "dn" else (160, 152)  # (5 MS-SSIM scales with a 19-tap window need >= 304 HR pixels)
+    xs = [torch.rand(2, 1, h, w, generator=g).to(dev) for _ in range(4)]
+    ts = [(torch.rand(2, 1, h * s, w * s, generator=g) * 0.5).to(dev) for _ in range(4)]
+    steps = []
+    for use_graph in (False, True):
+        m = _model(kind, 32, 1, sd, dev)
+        steps.append(TrainStep(m, create_loss(O.sc_dict_for("sqrt"), weights), lr=1e-4, use_graph=use_graph))
+    a, b = steps
+    for x, t in zip(xs, ts):
+        b.flat.copy_(a.flat)
+        b.opt.exp_avg.copy_(a.opt.exp_avg)
+        b.opt.exp_avg_sq.copy_(a.opt.exp_avg_sq)
+        b.engine.arena.invalidate()
+        la, lb = a(x, t), b(x, t)
+        assert abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))
+        assert rel_l2(b.engine.last_flat_grad, a.engine.last_flat_grad) < 1e-5
+    assert b._graph is not None and a._graph is None

@@ -760,11 +760,14 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
     WgradRole& w = a.roles[r];
     w.tap_begin = q.tap_begin; w.tap_count = q.tap_count; w.x_c0 = q.x_c0; w.x_boxes = q.x_boxes;
     w.y_c0 = q.y_c0; w.n = q.n; w.y_boxes = (q.n + 63) / 64; w.mode = q.mode;
+    static const int rows8_env = [] { const char* e = getenv("XMM_WG_ROWS8"); return e ? atoi(e) : 1; }();
+    w.rows8 = (q.mode == 0 && rows8_env && q.tap_begin / 3 == (q.tap_begin + q.tap_count - 1) / 3) ? 1 : 0;
     const double per_mma = q.n / 2.0 > 47.0 ? q.n / 2.0 : 47.0;  // measured tcgen05 floor, profiles/r01_probe1
     cost[r] = q.tap_count * per_mma * (q.mode == 1 ? wg_stacked_cost_scale() : 1.0);
     total += cost[r];
     const size_t st = q.mode == 1 ? size_t(w.x_boxes) * kWgBoxYBytes + size_t(kWgBoxX32Bytes)
-                                  : size_t(w.x_boxes) * kWgBoxXBytes + size_t(w.y_boxes) * kWgBoxYBytes;
+                                  : size_t(w.x_boxes) * (w.rows8 ? kWgBoxX8Bytes : kWgBoxXBytes) +
+                                        size_t(w.y_boxes) * kWgBoxYBytes;
     if (st > max_stage) max_stage = st;
   }
   int assigned = 0;
@@ -815,10 +818,12 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
     XMM_REQUIRE(q.o_begin >= 0 && q.o_begin + q.o_count <= d.o_total, "wgrad: destination %d output-channel window", i);
   }
 
-  CUtensorMap tx, ty, tx32;
+  CUtensorMap tx, ty, tx32, tx8;
   rc = cached_tmap(&tx, p.x, p.batch, p.height, p.width, p.x_ctot, 64, kTileW + 2, kWgTileH + 2);
   if (rc != XMM_OK) return rc;
   rc = cached_tmap(&tx32, p.x, p.batch, p.height, p.width, p.x_ctot, 32, kTileW + 2, kWgTileH + 2);  // SWIZZLE_64B
+  if (rc != XMM_OK) return rc;
+  rc = cached_tmap(&tx8, p.x, p.batch, p.height, p.width, p.x_ctot, 64, kTileW + 2, kWgTileH);  // single-filter-row roles
   if (rc != XMM_OK) return rc;
   rc = cached_tmap(&ty, p.dy, p.batch, p.height, p.width, p.dy_ctot, 64, kTileW, kWgTileH);
   if (rc != XMM_OK) return rc;
@@ -829,7 +834,7 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
     attr_set = true;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  wgrad_tc_kernel<<<dev.sm_count, kWgThreads, smem, s>>>(tx, ty, tx32, a);
+  wgrad_tc_kernel<<<dev.sm_count, kWgThreads, smem, s>>>(tx, ty, tx32, tx8, a);
   XMM_CUDA_OK(cudaGetLastError());
   wgrad_reduce_kernel<<<dim3(24, p.ndst), 256, 0, s>>>(ra, a.num_tiles);
   XMM_CUDA_OK(cudaGetLastError());

@@ -238,12 +238,14 @@ class CompositeLoss(nn.Module):
         n, b = st["n"], st["b"]
         dev = preds.device
         coef = torch.zeros(3, dtype=torch.float32, device=dev)
+        # (fill_ / copy_ of device values only: a Python scalar assigned into a CUDA tensor is a host-to-device copy,
+        # which a CUDA-graph capture of the training step rejects)
         if "l1" in self.weights:
-            coef[0] = self.weights["l1"] / n
+            coef[0:1].fill_(self.weights["l1"] / n)
         if "poisson" in self.weights:
-            coef[1] = self.weights["poisson"] / (n * b)
+            coef[1:2].fill_(self.weights["poisson"] / (n * b))
         if "psnr" in self.weights:
-            coef[2] = (self.weights["psnr"] * (-20.0 / math.log(10.0)) / n) / st["mse"]
+            coef[2:3].copy_(((self.weights["psnr"] * (-20.0 / math.log(10.0)) / n) / st["mse"]).reshape(1))
         grad = torch.empty_like(preds)
         _lib_call("xmm_loss_grad", preds.data_ptr(), target.data_ptr(), n, coef.data_ptr(), gl.data_ptr(),
                   grad.data_ptr(), 0)

@@ -14,6 +14,8 @@ gradients.
 """
 from __future__ import annotations
 
+import gc
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -101,7 +103,12 @@ class TrainStep:
     """forward + loss + backward + gradient all-reduce + Adam for one (lr, hr) batch."""
 
     def __init__(self, model: nn.Module, loss, lr: float = 1e-4, betas=(0.9, 0.999), group=None,
-                 overlap_allreduce: bool = True) -> None:
+                 overlap_allreduce: bool = True, use_graph: Optional[bool] = None) -> None:
+        """use_graph: replay forward + loss + backward (~800 launches, ~95 % GPU-busy when launched through Python) as
+        ONE CUDA graph per input shape; Adam and the running loss state stay outside.  Off by default
+        (XMM_TRAIN_GRAPH=1 enables): measured on B200 the eager step is already GPU-bound (362 vs 363 img/s, DN
+        training, profiles/r01_bench_train_graph_ab.log); it pays with a slow host.  Single-process runs only: with a
+        process group the NCCL chunks are issued eagerly."""
         import torch.distributed as dist
 
         self.model, self.loss, self.group = model, loss, group
@@ -115,6 +122,11 @@ class TrainStep:
         self._ones = torch.ones(1, dtype=torch.float32, device=self.flat.device)
         # chunk boundaries of the flat buffer: one chunk per RRDB (parameters are registered in module order)
         self._chunks = self._rrdb_chunks()
+        if use_graph is None:
+            use_graph = os.environ.get("XMM_TRAIN_GRAPH", "0") == "1"
+        self.use_graph = bool(use_graph) and self.world == 1
+        self._graph = None      # (key, CUDAGraph, static lr, static hr, loss state, flat gradient)
+        self._seen_key = None   # shapes of the last eager step (the capture follows one eager step of that shape)
 
     def _rrdb_chunks(self):
         offs, off = {}, 0
@@ -140,12 +152,12 @@ class TrainStep:
         else:
             dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
 
-    def __call__(self, lr_img: torch.Tensor, hr_img: torch.Tensor) -> torch.Tensor:
+    def _fwd_bwd(self, lr_img: torch.Tensor, hr_img: torch.Tensor):
+        """forward + loss + backward (+ the gradient all-reduce chunks); returns (loss state, flat gradient)."""
         eng = self.engine
         out, bufs = eng.forward_train(lr_img)
         # Model.forward's second clamp (models/model.py:49) is the identity on an output already in [0,1]
         st = self.loss._evaluate(out, hr_img.contiguous().float())
-        self.loss._merge(st)
         gout = self.loss._gradient(out, hr_img.contiguous().float(), st, self._ones)
         done = [len(self.flat)]  # upper end of the not-yet-reduced tail of the flat buffer
 
@@ -161,5 +173,27 @@ class TrainStep:
         for w in self._works:
             w.wait()
         self._works.clear()
+        return st, flat_grad
+
+    def __call__(self, lr_img: torch.Tensor, hr_img: torch.Tensor) -> torch.Tensor:
+        key = (tuple(lr_img.shape), tuple(hr_img.shape), lr_img.dtype, hr_img.dtype)
+        if self.use_graph and self._graph is not None and self._graph[0] == key:
+            _, graph, s_lr, s_hr, st, flat_grad = self._graph
+            s_lr.copy_(lr_img)
+            s_hr.copy_(hr_img)
+            graph.replay()
+        elif self.use_graph and self._seen_key == key and not torch.cuda.is_current_stream_capturing():
+            # second step of this shape: every lazily created buffer / tensor map / function attribute exists now
+            s_lr, s_hr = lr_img.clone(), hr_img.clone()
+            gc.collect()  # nothing may release device memory in mid-capture
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st, flat_grad = self._fwd_bwd(s_lr, s_hr)
+            self._graph = (key, graph, s_lr, s_hr, st, flat_grad)
+            graph.replay()
+        else:
+            self._seen_key = key
+            st, flat_grad = self._fwd_bwd(lr_img, hr_img)
+        self.loss._merge(st)
         self.opt.step(flat_grad, 1.0 / self.world)
         return st["total"]
