@@ -340,6 +340,61 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
   w.par ^= 1;
 }
 
+// This CTA's tiles as RUNS of consecutive tiles of the strip-major order.
+//   round-robin part: while a full round of gridDim.x strips is left, run r = strip blockIdx.x + r * gridDim.x;
+//   tail: the tiles that are left (all of them for small problems) are cut into gridDim.x equal contiguous ranges; a
+//         range that starts mid-strip begins one tile early with a "pre-tile" (outputs suppressed, carry established).
+// (With whole strips only, 832 strips on 148 CTAs -- batch 16 -- make 92 CTAs walk 6 strips and 56 walk 5.)
+// CTA pairs run in lock step and keep whole strips: both CTAs take the leader's count, a missing strip is a dummy.
+struct DxRuns {
+  int rr_runs, nruns;
+  int rr_r0, rr_step, rr_len;      // round-robin runs
+  int tail_g0, tail_t0, tail_len;  // tail run (tail_len > 0)
+  int dummy_from;                  // pair mode: runs >= dummy_from repeat run 0 with nothing stored
+  template <bool PAIR>
+  __device__ __forceinline__ void init(const ConvArgs& args) {
+    const int grid = int(gridDim.x), b = int(blockIdx.x);
+    const int nstrips = args.num_tiles / args.tiles_x;
+    rr_step = grid * args.tiles_x;
+    rr_len = args.tiles_x;
+    rr_r0 = b * args.tiles_x;
+    tail_len = 0;
+    tail_g0 = tail_t0 = 0;
+    if (PAIR) {
+      const int lead = b & ~1;
+      rr_runs = nstrips > lead ? (nstrips - lead + grid - 1) / grid : 0;
+      dummy_from = nstrips > b ? (nstrips - b + grid - 1) / grid : 0;
+      nruns = rr_runs;
+      return;
+    }
+    rr_runs = args.strip_rr ? nstrips / grid : 0;
+    dummy_from = 1 << 30;
+    const long long done = (long long)rr_runs * rr_step;
+    const long long rem = (long long)args.num_tiles - done;
+    const int t0 = int(done + rem * b / grid), t1 = int(done + rem * (b + 1) / grid);
+    if (t1 > t0) {
+      tail_t0 = t0;
+      tail_g0 = (t0 % args.tiles_x != 0) ? t0 - 1 : t0;
+      tail_len = t1 - tail_g0;
+    }
+    nruns = rr_runs + (tail_len > 0 ? 1 : 0);
+  }
+  // run -> first tile, tile count, first tile whose outputs are stored (tiles before it are pre-tiles), dummy?
+  __device__ __forceinline__ void get(int run, int& r0, int& len, int& tvalid, bool& dummy) const {
+    dummy = run >= dummy_from;
+    if (run < rr_runs) {
+      r0 = dummy ? rr_r0 : rr_r0 + run * rr_step;
+      len = rr_len;
+      tvalid = r0;
+    } else {
+      r0 = tail_g0;
+      len = tail_len;
+      tvalid = tail_t0;
+    }
+  }
+  __device__ __forceinline__ int total_tiles() const { return rr_runs * rr_len + tail_len; }
+};
+
 // Tensor maps of the side inputs (mask, r1, r2) that are staged through shared memory (ConvArgs::side_mask).
 struct DxSideMaps {
   CUtensorMap m[3];
@@ -413,20 +468,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  // This CTA's tiles: runs of consecutive tiles [g, run_end) of the strip-major order.  Contiguous mode: one run
-  // [t0, t1) (+ the pre-tile g0 = t0 - 1 when it starts mid-strip).  Round-robin mode: one run per strip
-  // blockIdx.x, blockIdx.x + gridDim.x, ...
-  const long long total = args.num_tiles;
-  const bool rr = args.strip_rr != 0;
-  const int t0 = rr ? int(blockIdx.x) * args.tiles_x : int(total * blockIdx.x / gridDim.x);
-  const int t1 = rr ? int(total) : int(total * (blockIdx.x + 1) / gridDim.x);
-  const int g0 = (!rr && t0 % args.tiles_x != 0) ? t0 - 1 : t0;
-  const int run_len = rr ? args.tiles_x : (t1 - g0);                 // tiles per run
-  const int run_step = rr ? int(gridDim.x) * args.tiles_x : (t1 - g0 > 0 ? t1 - g0 : 1);  // distance between runs
-  // Number of runs.  A pair runs in lock step: both CTAs take the leader's count (>= the peer's); a run past this
-  // CTA's last strip is a dummy (its first strip again, nothing stored).
-  const int lead_g0 = PAIR ? int(blockIdx.x & ~1u) * args.tiles_x : g0;
-  const int nruns = t1 > lead_g0 ? (t1 - lead_g0 + run_step - 1) / run_step : 0;
+  DxRuns runs;
+  runs.template init<PAIR>(args);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -455,9 +498,10 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       uint32_t phase = 0;
       int sbuf = 0;
       uint32_t sphase = 0;
-      for (int run = 0; run < nruns; ++run) {
-        const bool dummy = g0 + run * run_step >= t1;
-        const int r0 = dummy ? g0 : g0 + run * run_step;
+      for (int run = 0; run < runs.nruns; ++run) {
+        int r0, run_len, t0;
+        bool dummy;
+        runs.get(run, r0, run_len, t0, dummy);
         DxTile t(r0, args.tiles_x, args.tiles_y);
         for (int g = r0; g < r0 + run_len; ++g, t.next(args.tiles_x, args.tiles_y)) {
           const int y0 = t.ty * kDxTileH - 1, x0 = t.tx * kDxTileW;
@@ -514,7 +558,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       XMM_PROF_START(3);
-      const int my_tiles = nruns * run_len;
+      const int my_tiles = runs.total_tiles();
       for (int g = 0; g < my_tiles; ++g) {
         XMM_PROF_T0();
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -560,9 +604,10 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     uint32_t acc_phase = 0;
     int sbuf = 0;
     uint32_t sphase = 0;
-    for (int run = 0; run < nruns; ++run) {
-      const bool dummy = g0 + run * run_step >= t1;
-      const int r0 = dummy ? g0 : g0 + run * run_step;
+    for (int run = 0; run < runs.nruns; ++run) {
+      int r0, run_len, t0;
+      bool dummy;
+      runs.get(run, r0, run_len, t0, dummy);
       DxTile t(r0, args.tiles_x, args.tiles_y);  // advanced incrementally: no divisions in the tile loop
       for (int g = r0; g < r0 + run_len; ++g) {
         XMM_PROF_T0();
