@@ -468,7 +468,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  DxRuns runs;
+  DxRuns runs{};
   runs.template init<PAIR>(args);
 
   if (warp == 0) {
