@@ -101,7 +101,7 @@ typedef struct {
   void* out; int out_ctot, out_coff;
   int pixel_shuffle;  /* 1: out is [batch][2*height][2*width][out_ctot], cout/4 channels;
                          2: inverse -- out is [batch][height/2][width/2][out_ctot], 4*cout ch. */
-  int tap_mode;       /* 0 = library default; 1..3 force a haloed-tap-view layout, 4 the column-scatter form, 5 / 6 the same without / with CTA pairs (tests / probes) */
+  int tap_mode;       /* 0 = library default; 1..3 force a haloed-tap-view layout, 4 the column-scatter form, 5 / 6 the same without / with CTA pairs, 7 / 8 with one / two epilogue groups (tests / probes) */
   float* colsum;      /* optional (cout == 32): colsum[n] += colsum_scale * sum over all pixels of the value written
                          to channel n -- the bias gradient whose integrand this data-gradient layer produces       */
   float colsum_scale;

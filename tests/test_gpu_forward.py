@@ -83,13 +83,14 @@ def test_conv3x3_cta_pairs_bit_identical_to_single_ctas(dev, cin, h):
     arena.ensure(dev)
     xd, rd = x.to(dev), res.to(dev)
     outs = []
-    for tap_mode in (6, 5):  # CTA pairs / single CTAs
+    for tap_mode in (6, 5, 8):  # CTA pairs / single CTAs / single CTAs with two epilogue groups (two strips in flight)
         out = torch.full((b, h, w, 64), 3.0, dtype=torch.bfloat16, device=dev)
         ops.conv3x3(xd, 0, cin, arena.ptr("c"), kc, cout, out, 32, lrelu=0.2, s0=0.2, r1=rd, r1_coff=0, s1=1.0,
                     tap_mode=tap_mode)
         torch.cuda.synchronize()
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[1], outs[2])
     xin = x[..., :cin].float().permute(0, 3, 1, 2)
     want = F.leaky_relu(F.conv2d(xin, wgt.to(torch.bfloat16).float(), bias, padding=1), 0.2) * 0.2 \
         + res.float().permute(0, 3, 1, 2)

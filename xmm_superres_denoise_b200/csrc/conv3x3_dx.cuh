@@ -63,7 +63,11 @@ constexpr int kDxPatchH = kDxTileH + 2;
 constexpr int kDxEpiWarps = 8;
 constexpr int kDxThreads = 64 + 32 * kDxEpiWarps;
 
-template <int KC, int NT>
+// G2: the eight epilogue warps form TWO GROUPS of four (one warp per TMEM lane quarter, all Cout columns each) that
+// work on DIFFERENT strips; the MMA warp alternates tiles between the two strips.  An epilogue pass costs a warp
+// ~1800 cycles per tile whatever the layer (about a quarter of it per-tile fixed cost), and with all eight warps on
+// every tile that pass -- not the MMA stream -- is the tile period for Cin <= 128.
+template <int KC, int NT, bool G2 = false>
 struct DxCfg {
   static_assert(KC == 32 || KC == 64, "K chunk is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B) channels");
   static_assert(NT == 32 || NT == 64, "column-scatter form is for Cout 32 / 64");
@@ -78,7 +82,9 @@ struct DxCfg {
   static constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, 3 * NT, 0, 0);
   static constexpr int kBiasBytes = NT * 4;
   static constexpr int kBarBytes = (2 * kMaxStages + 2 * 4 + 1) * 8 + 16;
-  static constexpr int kWarpCols = NT / 2;          // Cout columns owned by one epilogue warp
+  static constexpr int kGroups = G2 ? 2 : 1;
+  static constexpr int kTileWarps = kDxEpiWarps / kGroups;  // epilogue warps that share one tile
+  static constexpr int kWarpCols = G2 ? NT : NT / 2;  // Cout columns owned by one epilogue warp
   static constexpr int kWarpChunks = kWarpCols / 16;  // 16-column groups per tcgen05.ld / arithmetic pass
   // per-warp output staging tile for the TMA store: [2 rows][16 px] x kWarpCols bf16, swizzled (32 B / 64 B rows)
   static constexpr int kWarpOutBytes = 32 * kWarpCols * 2;
@@ -97,9 +103,9 @@ struct DxCfg {
 // Byte offset of 16-byte chunk k16 of warp-local pixel p (0..31) inside a warp's staging tile: rows of 32 B
 // (SWIZZLE_32B: chunk bit 4 ^= address bit 7) or 64 B (SWIZZLE_64B: chunk bits [4,6) ^= address bits [7,9)) --
 // the layout the output tensor map expects, and conflict-free for the warp's 16-byte stores.
-template <int NT>
+template <int WC>  // WC = columns per warp: 16 -> 32-byte rows, 32 -> 64-byte rows
 __device__ __forceinline__ uint32_t dx_out_offset(int p, int k16) {
-  if (NT == 32) return uint32_t(p * 32 + ((k16 ^ ((p >> 2) & 1)) << 4));
+  if (WC == 16) return uint32_t(p * 32 + ((k16 ^ ((p >> 2) & 1)) << 4));
   return uint32_t(p * 64 + ((k16 ^ ((p >> 1) & 3)) << 4));
 }
 
@@ -167,10 +173,10 @@ __device__ __forceinline__ void dx_issue_chunk(uint32_t d_addr, uint64_t adesc_s
 }
 
 // Per-warp constants of the epilogue.
-template <int KC, int NT>
+template <int KC, int NT, bool G2 = false>
 struct DxEpiWarp {
-  using Cfg = DxCfg<KC, NT>;
-  int lane, q, half, prow, pcol, col_w;
+  using Cfg = DxCfg<KC, NT, G2>;
+  int lane, q, half, group, prow, pcol, col_w;
   bool first_col, last_col;
   int src_l, src_r;
   uint32_t mail;       // shared-memory address of this warp's mailboxes (+ this lane's half-warp row)
@@ -184,7 +190,8 @@ struct DxEpiWarp {
   __device__ __forceinline__ void init(int warp, int lane_, const float* bias_s, uint8_t* out_s, uint8_t* mail_s) {
     lane = lane_;
     q = warp & 3;
-    half = (warp - 2) >> 2;
+    half = G2 ? 0 : (warp - 2) >> 2;   // which half of the Cout columns
+    group = G2 ? (warp - 2) >> 2 : 0;  // which of the two strips in flight
     prow = 2 * q + (lane >> 4);
     pcol = lane & 15;
     first_col = pcol == 0;
@@ -217,12 +224,12 @@ struct DxEpiWarp {
 //   pre         pre-tile: only the carry is produced
 //   has_pend    lane 15 holds an unfinished column from the previous tile of this CTA
 //   PAIR        `tempty` is the LEADER CTA's barrier: released through its shared::cluster address
-template <int KC, int NT, bool PAIR = false>
-__device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const ConvEpilogue& epi,
+template <int KC, int NT, bool PAIR = false, bool G2 = false>
+__device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT, G2>& w, const ConvEpilogue& epi,
                                                  const CUtensorMap* tmap_out, uint32_t t_addr, uint64_t* tempty, int b,
                                                  int ty, int tx, int tiles_x, bool pre, bool has_pend, bool direct, int H,
                                                  int W, const uint8_t* const* side_tiles = nullptr) {
-  using Cfg = DxCfg<KC, NT>;
+  using Cfg = DxCfg<KC, NT, G2>;
   const int y = ty * kDxTileH + w.prow;
   const int x = w.last_col ? tx * kDxTileW - 1 : tx * kDxTileW + w.pcol;
   const bool valid = (y < H) && (w.last_col ? has_pend : (!pre && x < W));
@@ -309,8 +316,8 @@ __device__ __forceinline__ void dx_epilogue_tile(DxEpiWarp<KC, NT>& w, const Con
           for (int i = 0; i < 16; ++i) w.csum[cc * 16 + i] += v[i];
         }
         const int p = (w.lane >> 4) * kDxTileW + ((w.pcol + 1) & 15);  // box pixel: lane 15 is the box's column 0
-        *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2)) = pack8(v);
-        *reinterpret_cast<uint4*>(stage + dx_out_offset<NT>(p, cc * 2 + 1)) = pack8(v + 8);
+        *reinterpret_cast<uint4*>(stage + dx_out_offset<Cfg::kWarpCols>(p, cc * 2)) = pack8(v);
+        *reinterpret_cast<uint4*>(stage + dx_out_offset<Cfg::kWarpCols>(p, cc * 2 + 1)) = pack8(v + 8);
       } else {
         conv_epilogue_cols<NT, 16>(epi, nullptr, v, col, b, y, x, H, W, epi.colsum != nullptr ? &w.csum[cc * 16] : nullptr);
       }
@@ -400,11 +407,12 @@ struct DxSideMaps {
   CUtensorMap m[3];
 };
 
-template <int KC, int NT, bool PAIR = false>
+template <int KC, int NT, bool PAIR = false, bool G2 = false>
 __global__ void __launch_bounds__(kDxThreads, 1)
 conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                   const __grid_constant__ DxSideMaps side_maps, const ConvArgs args) {
-  using Cfg = DxCfg<KC, NT>;
+  using Cfg = DxCfg<KC, NT, G2>;
+  static_assert(!(PAIR && G2), "CTA pairs and epilogue groups are separate experiments");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;
@@ -445,12 +453,12 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
     for (int a = 0; a < Cfg::kAccStages; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], PAIR ? 2 * kDxEpiWarps : kDxEpiWarps);
+      ptx::mbar_init(&tempty_bar[a], PAIR ? 2 * kDxEpiWarps : Cfg::kTileWarps);
     }
     ptx::mbar_init(w_bar, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&sfull_bar[a], 1);
-      ptx::mbar_init(&sempty_bar[a], kDxEpiWarps);
+      ptx::mbar_init(&sempty_bar[a], Cfg::kTileWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -470,6 +478,11 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 
   DxRuns runs{};
   runs.template init<PAIR>(args);
+  // Issue order.  A UNIT is one run -- or, with two epilogue groups, two consecutive round-robin runs (strips) whose
+  // tiles alternate A0 B0 A1 B1 ...: group 0 takes A, group 1 takes B.  The tail run is never paired.
+  const int npairs = G2 ? runs.rr_runs / 2 : 0;
+  const int nunits = runs.nruns - npairs;
+  // tile counter c -> accumulator stage c % kAccStages, side-tile counter sc -> buffer sc & 1
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -498,47 +511,58 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       uint32_t phase = 0;
       int sbuf = 0;
       uint32_t sphase = 0;
-      for (int run = 0; run < runs.nruns; ++run) {
-        int r0, run_len, t0;
-        bool dummy;
-        runs.get(run, r0, run_len, t0, dummy);
-        DxTile t(r0, args.tiles_x, args.tiles_y);
-        for (int g = r0; g < r0 + run_len; ++g, t.next(args.tiles_x, args.tiles_y)) {
-          const int y0 = t.ty * kDxTileH - 1, x0 = t.tx * kDxTileW;
-          for (int ch = 0; ch < args.nchunks; ++ch) {
-            XMM_PROF_T0();
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            XMM_PROF_ADD(0);
-            if (PAIR) {  // both CTAs' stages complete on the leader's barrier
-              if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              ptx::tma_load_4d_pair(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in,
-                                    ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0), args.cin_off + ch * KC, x0, y0, t.b);
-            } else {
-              ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              ptx::tma_load_4d(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in, &full_bar[stage],
-                               args.cin_off + ch * KC, x0, y0, t.b);
-            }
-            if (++stage == args.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+      auto load_tile = [&](const DxTile& t, bool with_sides) {
+        const int y0 = t.ty * kDxTileH - 1, x0 = t.tx * kDxTileW;
+        for (int ch = 0; ch < args.nchunks; ++ch) {
+          XMM_PROF_T0();
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          XMM_PROF_ADD(0);
+          if (PAIR) {  // both CTAs' stages complete on the leader's barrier
+            if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            ptx::tma_load_4d_pair(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in,
+                                  ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0), args.cin_off + ch * KC, x0, y0, t.b);
+          } else {
+            ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            ptx::tma_load_4d(stage_s + size_t(stage) * Cfg::kStageBytes, &tmap_in, &full_bar[stage],
+                             args.cin_off + ch * KC, x0, y0, t.b);
           }
-          if (nside > 0 && g >= t0 && !dummy) {  // the output pixels' mask / residual tiles (not for pre-tiles)
-            ptx::mbar_wait(&sempty_bar[sbuf], sphase ^ 1u);
-            ptx::mbar_expect_tx(&sfull_bar[sbuf], uint32_t(nside) * Cfg::kSideTileBytes);
-            uint8_t* dst = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
-            const int coff[3] = {args.epi.mask_coff, args.epi.r1_coff, args.epi.r2_coff};
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (with_sides) {  // the output pixels' mask / residual tiles (not for pre-tiles)
+          ptx::mbar_wait(&sempty_bar[sbuf], sphase ^ 1u);
+          ptx::mbar_expect_tx(&sfull_bar[sbuf], uint32_t(nside) * Cfg::kSideTileBytes);
+          uint8_t* dst = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
+          const int coff[3] = {args.epi.mask_coff, args.epi.r1_coff, args.epi.r2_coff};
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-              if (args.side_mask & (1 << k)) {
-                ptx::tma_load_4d(dst, &side_maps.m[k], &sfull_bar[sbuf], coff[k], t.tx * kDxTileW - 1, t.ty * kDxTileH,
-                                 t.b);
-                dst += Cfg::kSideTileBytes;
-              }
-            if (++sbuf == 2) {
-              sbuf = 0;
-              sphase ^= 1u;
+          for (int k = 0; k < 3; ++k)
+            if (args.side_mask & (1 << k)) {
+              ptx::tma_load_4d(dst, &side_maps.m[k], &sfull_bar[sbuf], coff[k], t.tx * kDxTileW - 1, t.ty * kDxTileH,
+                               t.b);
+              dst += Cfg::kSideTileBytes;
             }
+          if (++sbuf == 2) {
+            sbuf = 0;
+            sphase ^= 1u;
+          }
+        }
+      };
+      for (int u = 0; u < nunits; ++u) {
+        const bool paired = u < npairs;
+        const int run_a = paired ? 2 * u : u + npairs;
+        int r0, run_len, t0, r0b = 0, len_b, t0b;
+        bool dummy, dummy_b;
+        runs.get(run_a, r0, run_len, t0, dummy);
+        if (paired) runs.get(run_a + 1, r0b, len_b, t0b, dummy_b);
+        DxTile t(r0, args.tiles_x, args.tiles_y), tb(r0b, args.tiles_x, args.tiles_y);
+        for (int g = r0; g < r0 + run_len; ++g) {
+          load_tile(t, nside > 0 && g >= t0 && !dummy);
+          t.next(args.tiles_x, args.tiles_y);
+          if (paired) {
+            load_tile(tb, nside > 0);
+            tb.next(args.tiles_x, args.tiles_y);
           }
         }
       }
@@ -597,55 +621,65 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   } else {
     // ------------------------------------------------------------ epilogue
     ptx::mbar_wait(w_bar, 0);
-    DxEpiWarp<KC, NT> w;
+    DxEpiWarp<KC, NT, G2> w;
     w.init(warp, lane, bias_s, out_s, mail_s);
     const bool direct = args.epi.pixel_shuffle != 0;  // (inverse) pixel shuffle scatters: direct stores
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int sbuf = 0;
-    uint32_t sphase = 0;
-    for (int run = 0; run < runs.nruns; ++run) {
+    constexpr int kAccShift = Cfg::kAccStages == 4 ? 2 : 1;
+    // one tile: c = its position in the issue order, sc = position among the tiles with side inputs
+    auto process = [&](const DxTile& t, int g, int r0, int t0, bool dummy, int c, int sc) {
+      const int acc = c & (Cfg::kAccStages - 1);
+      const uint32_t acc_phase = uint32_t(c >> kAccShift) & 1u;
+      XMM_PROF_T0();
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      XMM_PROF_ADD(4);
+      XMM_PROF_T0();
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(w.q * 32) << 16) + uint32_t(acc * Cfg::kAccCols);
+      const bool sides = nside > 0 && g >= t0 && !dummy;
+      const int sbuf = sc & 1;
+      const uint8_t* side_tiles[3] = {nullptr, nullptr, nullptr};
+      if (sides) {
+        ptx::mbar_wait(&sfull_bar[sbuf], uint32_t(sc >> 1) & 1u);
+        const uint8_t* src = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (args.side_mask & (1 << k)) {
+            // tile 0 of a strip stores (and reads its side inputs) directly: see dx_epilogue_tile
+            side_tiles[k] = src;
+            src += Cfg::kSideTileBytes;
+          }
+      }
+      dx_epilogue_tile<KC, NT, PAIR, G2>(w, args.epi, &tmap_out, t_addr, &tempty_bar[acc], t.b, t.ty, t.tx, args.tiles_x,
+                                         /*pre=*/g < t0 || dummy, /*has_pend=*/(t.tx > 0) && (g != r0) && !dummy,
+                                         direct, args.height, args.width, sides ? side_tiles : nullptr);
+      if (sides) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&sempty_bar[sbuf]);
+      }
+      XMM_PROF_ADD(5);
+    };
+    int c = 0, sc = 0;
+    for (int u = 0; u < nunits; ++u) {
+      const bool paired = u < npairs;
+      const int run_a = paired ? 2 * u : u + npairs;
       int r0, run_len, t0;
       bool dummy;
-      runs.get(run, r0, run_len, t0, dummy);
+      runs.get(paired ? run_a + w.group : run_a, r0, run_len, t0, dummy);
       DxTile t(r0, args.tiles_x, args.tiles_y);  // advanced incrementally: no divisions in the tile loop
-      for (int g = r0; g < r0 + run_len; ++g) {
-        XMM_PROF_T0();
-        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-        XMM_PROF_ADD(4);
-        XMM_PROF_T0();
-        ptx::tc_fence_after();
-        const uint32_t t_addr = tmem_base + (uint32_t(w.q * 32) << 16) + uint32_t(acc * Cfg::kAccCols);
-        const bool sides = nside > 0 && g >= t0 && !dummy;
-        const uint8_t* side_tiles[3] = {nullptr, nullptr, nullptr};
-        if (sides) {
-          ptx::mbar_wait(&sfull_bar[sbuf], sphase);
-          const uint8_t* src = side_s + size_t(sbuf * nside) * Cfg::kSideTileBytes;
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (args.side_mask & (1 << k)) {
-              // tile 0 of a strip stores (and reads its side inputs) directly: see dx_epilogue_tile
-              side_tiles[k] = src;
-              src += Cfg::kSideTileBytes;
-            }
+      if (paired) {  // this group's strip: every second tile of the issue order
+        for (int g = r0; g < r0 + run_len; ++g) {
+          process(t, g, r0, t0, dummy, c + w.group, sc + w.group);
+          c += 2;
+          sc += nside > 0 ? 2 : 0;
+          t.next(args.tiles_x, args.tiles_y);
         }
-        dx_epilogue_tile<KC, NT, PAIR>(w, args.epi, &tmap_out, t_addr, &tempty_bar[acc], t.b, t.ty, t.tx, args.tiles_x,
-                                       /*pre=*/g < t0 || dummy, /*has_pend=*/(t.tx > 0) && (g != r0) && !dummy, direct,
-                                       args.height, args.width, sides ? side_tiles : nullptr);
-        if (sides) {
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&sempty_bar[sbuf]);
-          if (++sbuf == 2) {
-            sbuf = 0;
-            sphase ^= 1u;
-          }
+      } else {       // a single run: group 0 (group 1 only keeps count)
+        for (int g = r0; g < r0 + run_len; ++g) {
+          if (w.group == 0) process(t, g, r0, t0, dummy, c, sc);
+          c += 1;
+          sc += (nside > 0 && g >= t0 && !dummy) ? 1 : 0;
+          t.next(args.tiles_x, args.tiles_y);
         }
-        XMM_PROF_ADD(5);
-        if (++acc == Cfg::kAccStages) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
-        t.next(args.tiles_x, args.tiles_y);
       }
     }
     if (ptx::elect_one()) ptx::bulk_wait<0>();  // this warp's stores complete before the CTA (and its smem) goes away

@@ -157,9 +157,9 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
 }
 
 // Row-gather / column-scatter form (conv3x3_dx.cuh): the default for Cout = 32 / 64.
-template <int KC, int NT>
-int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
-  using Cfg = DxCfg<KC, NT>;
+template <int KC, int NT, bool G2>
+int launch_conv_dx_impl(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  using Cfg = DxCfg<KC, NT, G2>;
   ConvArgs a{};
   a.wblob = p.wblob;
   a.nchunks = p.cin / KC;
@@ -213,7 +213,7 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   }
   static bool attr_set = false;
   if (!attr_set) {
-    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT, false, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      dev.max_smem_optin));
     attr_set = true;
   }
@@ -227,6 +227,7 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
   // TPC).  Opt-in (XMM_DX_PAIR=1): bit-identical and the MMA stream gets cheaper (49 vs 56 cycles), but the layers are
   // epilogue- (cin <= 96) or HBM-bound (cin >= 128), so the launch is not faster (profiles/r01_conv_prof_pair.log).
   static const int pair_env = [] { const char* e = getenv("XMM_DX_PAIR"); return e ? atoi(e) : 0; }();
+  if constexpr (!G2)
   if (KC == 32 && NT == 32 && (pair_env || p.tap_mode == 6) && p.tap_mode != 5 && a.strip_rr && grid % 2 == 0 &&
       nstrips >= grid) {
     static bool pair_attr_set = false;
@@ -250,9 +251,31 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
     XMM_CUDA_OK(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<KC, NT, true>, tmap, tmap_out, sides, a));
     return XMM_OK;
   }
-  conv3x3_dx_kernel<KC, NT><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, sides, a);
+  conv3x3_dx_kernel<KC, NT, false, G2><<<grid, kDxThreads, smem, stream>>>(tmap, tmap_out, sides, a);
   XMM_CUDA_OK(cudaGetLastError());
   return XMM_OK;
+}
+
+// Many round-robin strips per CTA (>= 16: inference batches), Cout = 32: two epilogue groups, two strips in flight per
+// CTA (DxCfg::G2): +2.5 % at batch 64; with few strips the unpaired ones run at half the epilogue capacity (batch 16:
+// -5 %), so those keep the single group (profiles/r01_dx_two_group_epilogue.log).  XMM_DX_G2=0 / tap_mode 5..7: off.
+template <int KC, int NT>
+int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  if constexpr (NT == 32) {
+    static const int g2_env = [] { const char* e = getenv("XMM_DX_G2"); return e ? atoi(e) : 1; }();
+    static const int rr_env = [] { const char* e = getenv("XMM_DX_RR"); return e ? atoi(e) : -1; }();
+    const int tiles_x = (p.width + kDxTileW - 1) / kDxTileW, tiles_y = (p.height + kDxTileH - 1) / kDxTileH;
+    const long long ntiles = (long long)tiles_x * tiles_y * p.batch, nstrips = (long long)tiles_y * p.batch;
+    const long long grid = ntiles < dev.sm_count ? ntiles : dev.sm_count;
+    const int nchunks = p.cin / KC;
+    const bool rr = rr_env >= 0 ? (rr_env != 0) : (nstrips >= 4LL * grid && (nchunks >= 3 || nstrips >= 16LL * grid));
+    const bool g2 = (p.tap_mode == 8) || (g2_env && rr && nstrips >= 16LL * grid && (p.tap_mode <= 0 || p.tap_mode == 4));
+    if (g2 && DxCfg<KC, NT, true>::smem_bytes(uint32_t(nchunks) * 9u * DxCfg<KC, NT, true>::kTapBytes, 4,
+                                               (p.mask != nullptr) + (p.r1 != nullptr) + (p.r2 != nullptr)) <=
+                  size_t(dev.max_smem_optin))
+      return launch_conv_dx_impl<KC, NT, true>(p, dev, stream);
+  }
+  return launch_conv_dx_impl<KC, NT, false>(p, dev, stream);
 }
 
 template <int KC, int NT>
@@ -313,7 +336,7 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   const bool dx_auto = p.tap_mode <= 0 && p.kc == 32 && p.cout == 32 && p.cin >= 64 &&
                        DxCfg<32, 32>::smem_bytes(uint32_t(p.cin / 32) * 9u * DxCfg<32, 32>::kTapBytes, 4) <=
                            size_t(dev.max_smem_optin);  // >= 4 pipeline stages next to the resident weights
-  if (p.tap_mode == 4 || p.tap_mode == 5 || p.tap_mode == 6 || dx_auto) {  // 5 / 6: without / with CTA pairs
+  if ((p.tap_mode >= 4 && p.tap_mode <= 8) || dx_auto) {  // 5 / 6: without / with CTA pairs, 7 / 8: one / two epilogue groups
     if (p.kc == 32 && p.cout == 32) return launch_conv_dx<32, 32>(p, dev, s);
     if (p.kc == 64 && p.cout == 64) return launch_conv_dx<64, 64>(p, dev, s);
     return fail(XMM_ERR_INVALID_ARGUMENT, "conv3x3: the column-scatter form is built for cout = kc = 32 or 64");
