@@ -99,6 +99,43 @@ def test_conv3x3_cta_pairs_bit_identical_to_single_ctas(dev, cin, h):
     assert torch.all(outs[0][..., :32] == 3.0)
 
 
+def test_conv3x3_two_epilogue_groups_with_mask_residuals_and_bias_sums(dev):
+    """The data-gradient flavour of a layer (LeakyReLU' mask, two residuals, fused bias-gradient column sums) on a
+    many-strip problem: two epilogue groups (tap_mode 8) against one (tap_mode 7) -- same output bits, same sums."""
+    from xmm_superres_denoise_b200 import ops
+    from xmm_superres_denoise_b200.engine import WeightArena, _Blob, _Segment
+
+    g = torch.Generator().manual_seed(7)
+    b, h, w, cin, cout, kc = 1, 8 * 2400 + 3, 40, 96, 32, 32
+    x = torch.randn(b, h, w, 160, generator=g).to(torch.bfloat16)
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+    mask = torch.randn(b, h, w, 32, generator=g).to(torch.bfloat16)
+    r1 = torch.randn(b, h, w, 32, generator=g).to(torch.bfloat16)
+    r2 = torch.randn(b, h, w, 64, generator=g).to(torch.bfloat16)
+    arena = WeightArena()
+    wd = wgt.to(dev)
+    arena.add(_Blob("c", cout, kc, cin // kc, [_Segment(wd, cin, 0, 0, 0, 0, cin, 1.0)], None))
+    arena.ensure(dev)
+    xd, md, r1d, r2d = x.to(dev), mask.to(dev), r1.to(dev), r2.to(dev)
+    outs, sums = [], []
+    for tap_mode in (8, 7):
+        out = torch.zeros((b, h, w, 32), dtype=torch.bfloat16, device=dev)
+        cs = torch.zeros(32, device=dev)
+        ops.conv3x3(xd, 32, cin, arena.ptr("c"), kc, cout, out, 0, mask=md, mask_coff=0, mask_slope=0.2, r1=r1d, r1_coff=0,
+                    s1=1.0, r2=r2d, r2_coff=32, s2=0.5, colsum=cs, colsum_scale=0.2, tap_mode=tap_mode)
+        torch.cuda.synchronize()
+        outs.append(out)
+        sums.append(cs)
+    assert torch.equal(outs[0], outs[1])
+    assert rel_l2(sums[0].cpu(), sums[1].cpu()) < 1e-5  # (atomics: summation order differs)
+    xin = x[..., 32:32 + cin].float().permute(0, 3, 1, 2)
+    y = F.conv2d(xin, wgt.to(torch.bfloat16).float(), None, padding=1)
+    y = y * torch.where(mask.float().permute(0, 3, 1, 2) > 0, 1.0, 0.2)
+    want = y + r1.float().permute(0, 3, 1, 2) + 0.5 * r2[..., 32:].float().permute(0, 3, 1, 2)
+    assert rel_l2(outs[0].float().permute(0, 3, 1, 2).cpu(), want) < 4e-3
+    assert rel_l2(sums[0].cpu(), 0.2 * want.sum(dim=(0, 2, 3))) < 2e-2  # sums of bf16-rounded outputs
+
+
 def test_conv3x3_rejects_bad_arguments(dev):
     from xmm_superres_denoise_b200 import ops
 
