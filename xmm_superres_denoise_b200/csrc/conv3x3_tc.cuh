@@ -127,8 +127,10 @@ struct ConvCfg {
   // per-warp output staging for the TMA store ([4 rows][8 px] x NT bf16, swizzled; 4 warps, double buffered)
   static constexpr int kWarpOutBytes = (NT <= 64) ? 32 * NT * 2 : 0;
   static constexpr int kOutBytes = 4 * 2 * kWarpOutBytes;
-  static size_t smem_bytes(uint32_t w_bytes, int stages) {
-    return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + kOutBytes + kBarBytes;
+  // with_out: the per-warp staging tiles of the TMA-store path (ConvArgs::tma_store) are part of the layout
+  static size_t smem_bytes(uint32_t w_bytes, int stages, bool with_out = true) {
+    return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + (with_out ? kOutBytes : 0) +
+           kBarBytes;
   }
 };
 
@@ -282,7 +284,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   float* bias_s = reinterpret_cast<float*>(smem + args.w_bytes);         // NT floats (same bulk copy)
   uint8_t* stage_s = smem + ((args.w_bytes + Cfg::kBiasBytes + 1023) & ~1023u);
   uint8_t* out_s = stage_s + size_t(args.stages) * Cfg::kStageBytes;  // 1 KB aligned (stage sizes are)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_s + Cfg::kOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_s + (args.tma_store != 0 ? Cfg::kOutBytes : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;

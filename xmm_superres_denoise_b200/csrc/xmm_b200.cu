@@ -116,15 +116,26 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
   a.tiles_x = (p.width + kTileW - 1) / kTileW;
   a.tiles_y = (p.height + kTileH - 1) / kTileH;
   a.num_tiles = a.tiles_x * a.tiles_y * p.batch;
-  const size_t fixed = Cfg::smem_bytes(a.w_bytes, 0);
-  if (fixed + 2 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin))
+  // Plain NHWC outputs of narrow layers leave through per-warp TMA stores (XMM_TC_TMA_STORE=0: direct stores, 2: always) -- as
+  // long as their staging tiles (16 / 32 KB) do not cost the layer a pipeline stage it needs: the 64-filter layers with
+  // 74..147 KB of resident weights keep their stages instead (measured: F=64 inference 146 -> 160 img/s).
+  static const int tma_env = [] { const char* e = getenv("XMM_TC_TMA_STORE"); return e ? atoi(e) : 1; }();
+  const size_t fixed_plain = Cfg::smem_bytes(a.w_bytes, 0, false), fixed_out = Cfg::smem_bytes(a.w_bytes, 0, true);
+  if (fixed_plain + 2 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin))
     return fail(XMM_ERR_UNSUPPORTED_SHAPE,
                 "conv3x3: weights of cin=%d cout=%d (%u B) do not fit in shared memory next to 2 pipeline stages",
                 p.cin, p.cout, a.w_bytes);
-  int stages = int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes);
-  if (stages > kMaxStages) stages = kMaxStages;
+  auto stages_for = [&](size_t fixed) {
+    const int st = size_t(dev.max_smem_optin) > fixed ? int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes) : 0;
+    return st > kMaxStages ? kMaxStages : st;
+  };
+  const int st_plain = stages_for(fixed_plain), st_out = stages_for(fixed_out);
+  a.tma_store = (Cfg::kOutBytes > 0 && p.pixel_shuffle == 0 && img == nullptr && st_out >= 2 &&
+                 (tma_env == 2 || (tma_env == 1 && (st_out >= 6 || st_out == st_plain))))
+                    ? 1 : 0;
+  const int stages = a.tma_store ? st_out : st_plain;
   a.stages = stages;
-  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages);
+  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages, a.tma_store != 0);
 
   fill_epilogue(a.epi, p);
   if (img != nullptr) {
@@ -135,10 +146,7 @@ int launch_conv(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t
   CUtensorMap tmap;
   int rc = cached_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, KC, Cfg::kPitchPx, kHaloH);
   if (rc != XMM_OK) return rc;
-  // plain NHWC outputs of narrow layers leave through per-warp TMA stores (XMM_TC_TMA_STORE=0: direct stores)
-  static const int tma_env = [] { const char* e = getenv("XMM_TC_TMA_STORE"); return e ? atoi(e) : 1; }();
   CUtensorMap tmap_out = tmap;
-  a.tma_store = (Cfg::kOutBytes > 0 && p.pixel_shuffle == 0 && img == nullptr && tma_env) ? 1 : 0;
   if (a.tma_store) {
     rc = cached_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, NT, kTileW, 4);
     if (rc != XMM_OK) return rc;
@@ -270,7 +278,9 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
     const int nchunks = p.cin / KC;
     const bool rr = rr_env >= 0 ? (rr_env != 0) : (nstrips >= 4LL * grid && (nchunks >= 3 || nstrips >= 16LL * grid));
     const bool g2 = (p.tap_mode == 8) || (g2_env && rr && nstrips >= 16LL * grid && (p.tap_mode <= 0 || p.tap_mode == 4));
-    if (g2 && DxCfg<KC, NT, true>::smem_bytes(uint32_t(nchunks) * 9u * DxCfg<KC, NT, true>::kTapBytes, 4,
+    // (the second group's staging tiles cost 20 KB of shared memory: only where >= 6 activation stages remain)
+    if (g2 && DxCfg<KC, NT, true>::smem_bytes(uint32_t(nchunks) * 9u * DxCfg<KC, NT, true>::kTapBytes,
+                                               p.tap_mode == 8 ? 2 : 6,
                                                (p.mask != nullptr) + (p.r1 != nullptr) + (p.r2 != nullptr)) <=
                   size_t(dev.max_smem_optin))
       return launch_conv_dx_impl<KC, NT, true>(p, dev, stream);
