@@ -105,8 +105,13 @@ struct ConvArgs {
 #endif
 };
 
-template <int KC, int NT, int MODE>
+// EG = epilogue groups (1 or 2): groups of four epilogue warps take alternate tiles of the CTA's sequence (the tiles
+// are independent here: haloed patches, no carries), with 2 * EG accumulator stages in TMEM.
+template <int KC, int NT, int MODE, int EG = 1>
 struct ConvCfg {
+  static_assert(EG == 1 || EG == 2, "one or two epilogue groups");
+  static constexpr int kThreads = 64 + 128 * EG;
+  static constexpr int kAccStages = 2 * EG;
   static_assert(KC == 32 || KC == 64, "K chunk is 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B) channels");
   static_assert(NT % 32 == 0 && NT >= 32 && NT <= 256, "Cout tile");
   static constexpr int kRowB = KC * 2;  // bytes of one pixel's K-chunk in shared memory
@@ -119,14 +124,16 @@ struct ConvCfg {
   static constexpr int kStageTx = kNumSub * kSubBytes;
   static constexpr int kKSteps = KC / 16;
   static constexpr int kTapBytes = NT * kRowB;  // one (chunk, tap) weight block
-  static constexpr int kTmemCols = (2 * NT <= 32) ? 32 : (2 * NT <= 64) ? 64 : (2 * NT <= 128) ? 128 : (2 * NT <= 256) ? 256 : 512;
+  static_assert(2 * EG * NT <= 512, "accumulator stages exceed the 512 TMEM columns");
+  static constexpr int kTmemCols = (2 * EG * NT <= 32) ? 32 : (2 * EG * NT <= 64) ? 64 : (2 * EG * NT <= 128) ? 128
+                                   : (2 * EG * NT <= 256) ? 256 : 512;
   static constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, NT, 0, 0);
   static constexpr int kBiasBytes = NT * 4;
-  // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] wbar + tmem ptr
-  static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 16;
+  // barriers: full[8] empty[8] tmem_full[4] tmem_empty[4] wbar + tmem ptr
+  static constexpr int kBarBytes = (2 * kMaxStages + 9) * 8 + 16;
   // per-warp output staging for the TMA store ([4 rows][8 px] x NT bf16, swizzled; 4 warps, double buffered)
   static constexpr int kWarpOutBytes = (NT <= 64) ? 32 * NT * 2 : 0;
-  static constexpr int kOutBytes = 4 * 2 * kWarpOutBytes;
+  static constexpr int kOutBytes = 4 * EG * 2 * kWarpOutBytes;
   // with_out: the per-warp staging tiles of the TMA-store path (ConvArgs::tma_store) are part of the layout
   static size_t smem_bytes(uint32_t w_bytes, int stages, bool with_out = true) {
     return 1024 /*align slack*/ + w_bytes + kBiasBytes + 1024 + size_t(stages) * kStageBytes + (with_out ? kOutBytes : 0) +
@@ -273,11 +280,11 @@ __device__ __forceinline__ void colsum_flush(const ConvEpilogue& e, float (&csum
   }
 }
 
-template <int KC, int NT, int MODE>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int KC, int NT, int MODE, int EG = 1>
+__global__ void __launch_bounds__(64 + 128 * EG, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
                   const ConvArgs args) {
-  using Cfg = ConvCfg<KC, NT, MODE>;
+  using Cfg = ConvCfg<KC, NT, MODE, EG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;                                                   // weights image
@@ -288,8 +295,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* w_bar = tempty_bar + 2;
+  uint64_t* tempty_bar = tfull_bar + 4;
+  uint64_t* w_bar = tempty_bar + 4;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -308,7 +315,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < Cfg::kAccStages; ++a) {
       ptx::mbar_init(&tfull_bar[a], 1);
       ptx::mbar_init(&tempty_bar[a], 4);
     }
@@ -410,8 +417,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           }
         }
         ptx::umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == Cfg::kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
       XMM_PROF_STOP(3);
       XMM_PROF_FLUSH(1); XMM_PROF_FLUSH(2); XMM_PROF_FLUSH(3);
@@ -429,13 +438,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     uint8_t* my_out = out_s + (warp - 2) * 2 * Cfg::kWarpOutBytes;
     const uint32_t sw_xor = NT == 32 ? uint32_t((lane >> 1) & 3) : uint32_t(lane & 7);
     int obuf = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int group = (warp - 2) >> 2;  // which tiles of the sequence this warp's group takes
+    int seq = 0;                        // position in this CTA's tile sequence
     const bool do_csum = NT == 32 && args.epi.colsum != nullptr;
     float csum[NT == 32 ? 32 : 1];
 #pragma unroll
     for (int i = 0; i < (NT == 32 ? 32 : 1); ++i) csum[i] = 0.f;
-    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++seq) {
+      if (EG > 1 && (seq & (EG - 1)) != group) continue;
+      const int acc = seq & (Cfg::kAccStages - 1);
+      const uint32_t acc_phase = uint32_t(seq / Cfg::kAccStages) & 1u;
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
       const int ty = r / args.tiles_x;
@@ -512,8 +524,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         obuf ^= 1;
       }
       XMM_PROF_ADD(5);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
     if (use_tma && ptx::elect_one()) ptx::bulk_wait<0>();  // stores complete before the CTA (and its smem) goes away
     if (NT == 32 && do_csum) {
