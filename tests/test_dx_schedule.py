@@ -9,7 +9,6 @@ conv3x3_dx_kernel) restated in Python and checked for its invariants over many p
 
 The restatement follows the C++ line by line (same integer arithmetic); the GPU tests check the kernel itself
 (tests/test_gpu_forward.py::test_conv3x3_cta_pairs_bit_identical_to_single_ctas)."""
-import itertools
 
 import pytest
 
