@@ -10,8 +10,9 @@ Prints ONE JSON line on rank 0 (contract in the task statement): `value` is devi
 throughput, `e2e` the same metric through the public classes with pinned HOST buffers (H2D of the
 int32 counts + fused normalise + generator + D2H of the fp32 prediction inside the timed region),
 `roofline` the tensor-core fraction of the dominant kernel (dense-block conv3x3) from CUDA events
-recorded around every one of its launches in the timed region, `cpu_baseline` the oracle port
-(torch fp32 on the host cores) on a bounded sample.  `--impl reference` times that CPU path alone.
+recorded around every one of its launches in the timed region, `cpu_baseline` the reference's own
+classes (oracle/_ref; torch fp32 on the host cores) on a bounded sample.  `--impl reference` times that
+CPU path alone.  After the timed region one output image is checked against the oracle (`parity_rel_l2`).
 """
 from __future__ import annotations
 
@@ -140,51 +141,79 @@ def oracle_state_dict(kind: str):
     return O.init_state_dict(kind, 1, 1, NF, NB, 1, seed=21)
 
 
-def cpu_infer_sample(n_images: int, threads: int):
-    """Oracle port (torch fp32 CPU) SR inference incl. normalise; returns images/sec."""
+def cpu_forward_fn():
+    """The CPU arm's forward: the REFERENCE's own GeneratorRRDB_SR + Normalize (oracle/_ref, vendored from
+    /root/reference by `python -m oracle.make_ref`; kind "reference") when present, else the oracle port (kind
+    "port").  Returns (fn(counts_rate fp32 [B,1,416,416]) -> [B,1,832,832], kind, description)."""
+    from oracle import ref_loader
     from oracle import rrdb_oracle as O
 
-    torch.set_num_threads(threads)
     sd = oracle_state_dict("sr")
-    lr, _, t_lr, _ = synthetic_counts(1, 7, "sr")
-    x = torch.from_numpy(lr.astype(np.float32))
+    if ref_loader.available() and NF == 32 and NB == 4:
+        ref = ref_loader.load_reference()
+        model = ref.GeneratorRRDB_SR(in_channels=1, out_channels=1, num_filters=NF, num_res_blocks=NB, num_upsample=1)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        norm = ref.Normalize(lr_max=LR_MAX, hr_max=HR_MAX_SR, stretch_mode="sqrt")
+
+        def fwd(rate):
+            # models/model.py:48-49 (Model.forward): clamp(generator(x), 0, 1); data/dataset.py:258-270: normalise
+            return torch.clamp(model(norm.normalize_lr_image(rate.clone())), 0.0, 1.0)
+
+        return fwd, "reference", "reference classes GeneratorRRDB_SR + Normalize (%s copy), torch %s fp32 oneDNN" % (
+            ref_loader.source(), torch.__version__)
+
+    def fwd_port(rate):
+        return O.model_forward(O.normalize_image(rate, LR_MAX, "sqrt"), sd, "sr", 1)
+
+    return fwd_port, "port", "oracle port (oracle/_ref absent), torch %s fp32 oneDNN" % torch.__version__
+
+
+def cpu_infer_sample(n_steps: int, images_per_step: int, threads: int):
+    """CPU SR inference incl. normalise on a bounded sample; returns (images/sec, seconds, kind, description)."""
+    torch.set_num_threads(threads)
+    fwd, kind, desc = cpu_forward_fn()
+    lr, _, t_lr, _ = synthetic_counts(images_per_step, 7, "sr")
+    x = torch.from_numpy(lr.astype(np.float32)) / t_lr
     with torch.no_grad():
-        O.model_forward(O.normalize_image(x / t_lr, LR_MAX, "sqrt"), sd, "sr", 1)  # warm-up
+        fwd(x[:1])  # warm-up
         t0 = time.perf_counter()
-        for _ in range(n_images):
-            O.model_forward(O.normalize_image(x / t_lr, LR_MAX, "sqrt"), sd, "sr", 1)
+        for _ in range(n_steps):
+            fwd(x)
         dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return n_steps * images_per_step / dt, dt, kind, desc
+
+
+CPU_IMAGES_PER_STEP = 4  # bounded sample of the batch-64 workload: one step of the CPU arm = 4 images (~2.5 s on 16 cores)
 
 
 def run_reference(args, rank: int) -> None:
-    """--impl reference: the reference's CPU implementation of the path (oracle port: /root/reference is
-    Python and cannot travel to the GPU box), all host threads, one image per step."""
+    """--impl reference: the reference's own CPU implementation of the path (its GeneratorRRDB_SR / Normalize classes
+    from oracle/_ref; the oracle port only if that copy is missing), all host threads, 4 images per step."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    from oracle import rrdb_oracle as O
-
     torch.set_num_threads(threads)
-    sd = oracle_state_dict("sr")
-    lr, _, t_lr, _ = synthetic_counts(1, 7, "sr")
-    x = torch.from_numpy(lr.astype(np.float32))
+    fwd, kind, desc = cpu_forward_fn()
+    n = CPU_IMAGES_PER_STEP
+    lr, _, t_lr, _ = synthetic_counts(n, 7, "sr")
+    x = torch.from_numpy(lr.astype(np.float32)) / t_lr
     times = []
     with torch.no_grad():
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            O.model_forward(O.normalize_image(x / t_lr, LR_MAX, "sqrt"), sd, "sr", 1)
+            fwd(x)
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
-    value = args.steps / total
+    value = n * args.steps / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: XMM-SuperRes 2x RRDB inference (F=32, nb=4), CPU fp32",
-                       "sample": "1 image of 416x416 per step (bounded sample of the batch-64 workload)"},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps x 1 image, torch {torch.__version__} fp32 oneDNN"},
+                       "sample": "%d images of 416x416 per step (bounded sample of the batch-64 workload)" % n},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": kind,
+                             "sample": f"{args.steps} steps x {n} images, {desc}"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -480,10 +509,10 @@ def main() -> None:
     }
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         threads = os.cpu_count() or 1
-        ips, dt = cpu_infer_sample(8, threads)
-        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": "8 images of the same workload (%.1f s), oracle port: torch %s fp32 on CPU" % (
-                                    dt, torch.__version__)}
+        ips, dt, kind, desc = cpu_infer_sample(3, CPU_IMAGES_PER_STEP, threads)
+        line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
+                                "sample": "3 steps x %d images of the same workload (%.1f s), %s" % (
+                                    CPU_IMAGES_PER_STEP, dt, desc)}
     if train_extra:
         line["extra"] = train_extra
     print(json.dumps(line), flush=True)

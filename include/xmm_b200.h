@@ -70,6 +70,9 @@ typedef struct {
   int n_valid;        /* rows >= n_valid are zero                                          */
   int bias_n;         /* rows < bias_n take bias[seg[0].o_off + row]; the rest get 0               */
   xmm_pack_segment seg[5];
+  int tap_order;      /* order of the nine (chunk, tap) blocks: 0 = dy*3 + dx (tap views / column scatter),
+                         1 = dx*3 + (2 - dy): the three filter rows of one dx are one N = 3*nt operand whose
+                         blocks belong to output rows r-1, r, r+1 of input row r (row-hop form, wblob_row)  */
 } xmm_pack_job;
 
 /* Bytes of one packed blob. */
@@ -108,6 +111,10 @@ typedef struct {
   int shuffle_stride; /* pixel_shuffle == 2 only: channel distance between the four (y&1, x&1) blocks of the output
                          (0 = cout).  A layer split along its output channels writes part n0 with out_coff + n0 and
                          the full layer's cout here.                                                              */
+  const void* wblob_row; /* optional: the same layer packed with tap_order = 1.  When given, and the shape qualifies
+                         (cout == kc in {32, 64}, no pixel shuffle, height = nbands * band_h with 8 <= nbands <= 16,
+                         weights resident next to >= 3 pipeline stages), the launch takes the row-hop form
+                         (conv3x3_row.cuh); tap_mode 9 forces it (error if it does not qualify), 1..8 never use it. */
 } xmm_conv3x3_params;
 
 int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);

@@ -1,8 +1,9 @@
 """Import the reference's own classes from /root/reference by file path -- TEST INFRASTRUCTURE.
 
-Only usable in the authoring container (the reference tree does not exist on the GPU box);
-used by ``oracle/make_golden.py`` to generate ``tests/golden/*.npz`` and by the CPU tests that
-cross-check the oracle restatement against the live reference when it is present.
+In the authoring container this is the live tree; on the GPU box (no /root/reference) it is the copy of the four
+torch-only files that ``oracle/make_ref.py`` vendors into ``oracle/_ref/`` (git-ignored, not gpurun-ignored).  Used by
+``oracle/make_golden.py`` to generate ``tests/golden/*.npz``, by the tests that cross-check the oracle restatement and
+the CUDA path against the reference's own classes, and by ``bench.py --impl reference``.
 
 ``import models`` would pull ``models/model.py`` -> ``lightning`` (not installed), so the two
 network files and the two transform files are loaded individually behind a stub package.
@@ -15,11 +16,28 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("XMM_REFERENCE_ROOT", "/root/reference")
-_PKG = os.path.join(REF_ROOT, "xmm_superres_denoise")
+# the copy `python -m oracle.make_ref` vendors (git-ignored; travels to the GPU box with the snapshot)
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pkg_dir() -> str:
+    """The live reference tree when it is mounted, else the vendored copy under oracle/_ref."""
+    for root in (REF_ROOT, VENDORED_ROOT):
+        pkg = os.path.join(root, "xmm_superres_denoise")
+        if os.path.isfile(os.path.join(pkg, "models", "modules", "generator_rrdb.py")):
+            return pkg
+    return os.path.join(REF_ROOT, "xmm_superres_denoise")
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(_PKG, "models", "modules", "generator_rrdb.py"))
+    return os.path.isfile(os.path.join(_pkg_dir(), "models", "modules", "generator_rrdb.py"))
+
+
+def source() -> str:
+    """"live" (/root/reference), "vendored" (oracle/_ref) or "absent"."""
+    if not available():
+        return "absent"
+    return "live" if _pkg_dir().startswith(REF_ROOT) else "vendored"
 
 
 def _load(name: str, path: str):
@@ -33,7 +51,8 @@ def _load(name: str, path: str):
 def load_reference():
     """Returns a namespace with GeneratorRRDB_DN, GeneratorRRDB_SR, RRDB, Normalize, ImageUpsample."""
     if not available():
-        raise FileNotFoundError(f"reference tree not found under {REF_ROOT}")
+        raise FileNotFoundError(f"reference tree not found under {REF_ROOT} or {VENDORED_ROOT} (python -m oracle.make_ref)")
+    _PKG = _pkg_dir()
     saved = {k: sys.modules.get(k) for k in ("models", "models.modules")}
     try:
         pkg = types.ModuleType("models")

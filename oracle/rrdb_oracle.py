@@ -251,9 +251,10 @@ def psnr(preds: Tensor, target: Tensor) -> Tensor:
     return 10.0 * torch.log10(dr ** 2 / mse)
 
 
-def gaussian_window(sigma: float) -> Tensor:
+def gaussian_window(sigma: float, dtype: torch.dtype = torch.float32) -> Tensor:
+    """torchmetrics ``_gaussian``: built in the dtype of the images (fp32 in the reference)."""
     size = int(3.5 * sigma + 0.5) * 2 + 1
-    dist = torch.arange((1 - size) / 2, (1 + size) / 2, 1.0)
+    dist = torch.arange((1 - size) / 2, (1 + size) / 2, 1.0, dtype=dtype)
     g = torch.exp(-((dist / sigma) ** 2) / 2)
     return g / g.sum()
 
@@ -263,7 +264,7 @@ def ssim_sim_cs(preds: Tensor, target: Tensor, sigma: float = 2.5, k1: float = 0
     data_range=None, return_contrast_sensitivity=True; (B,1,H,W) -> per-image (sim, cs)."""
     dr = max(preds.max() - preds.min(), target.max() - target.min())
     c1, c2 = (k1 * dr) ** 2, (k2 * dr) ** 2
-    g = gaussian_window(sigma).to(preds.dtype)
+    g = gaussian_window(sigma, preds.dtype)
     pad = (g.numel() - 1) // 2
     c = preds.shape[1]
     kernel = (g[:, None] * g[None, :]).expand(c, 1, -1, -1)

@@ -136,6 +136,105 @@ def test_conv3x3_two_epilogue_groups_with_mask_residuals_and_bias_sums(dev):
     assert rel_l2(sums[0].cpu(), 0.2 * want.sum(dim=(0, 2, 3))) < 2e-2  # sums of bf16-rounded outputs
 
 
+def _row_case(dev, b, h, w, cin, in_coff, in_ctot, kc, cout, *, lrelu=1.0, mask=False, r1=False, r2=False, colsum=False,
+              seed=0):
+    """One layer through the row-hop form (tap_mode 9) against F.conv2d; returns (got, want, colsum got, want)."""
+    from xmm_superres_denoise_b200 import ops
+    from xmm_superres_denoise_b200.engine import WeightArena, _Blob, _Segment
+
+    g = torch.Generator().manual_seed(1000 * cin + h + seed)
+    x = torch.randn(b, h, w, in_ctot, generator=g).to(torch.bfloat16)
+    wgt = torch.randn(cout, cin, 3, 3, generator=g) * 0.05
+    bias = torch.randn(cout, generator=g) * 0.1
+    side = [torch.randn(b, h, w, cout + 32, generator=g).to(torch.bfloat16) for _ in range(3)]
+    arena = WeightArena()
+    wd, bd = wgt.to(dev), bias.to(dev)
+    arena.add(_Blob("c", cout, kc, cin // kc, [_Segment(wd, cin, 0, 0, 0, 0, cin, 1.0)], bd))
+    arena.add(_Blob("c.row", cout, kc, cin // kc, [_Segment(wd, cin, 0, 0, 0, 0, cin, 1.0)], bd, tap_order=1))
+    arena.ensure(dev)
+    out = torch.full((b, h, w, cout + 32), 3.0, dtype=torch.bfloat16, device=dev)
+    kw = dict(lrelu=lrelu, s0=0.2 if r1 else 1.0, tap_mode=9, wblob_row=arena.ptr("c.row"))
+    sd = [t.to(dev) for t in side]
+    if mask:
+        kw.update(mask=sd[0], mask_coff=32, mask_slope=0.2)
+    if r1:
+        kw.update(r1=sd[1], r1_coff=0, s1=1.0)
+    if r2:
+        kw.update(r2=sd[2], r2_coff=32, s2=0.5)
+    cs = torch.zeros(cout, device=dev) if colsum else None
+    if colsum:
+        kw.update(colsum=cs, colsum_scale=0.2)
+    ops.conv3x3(x.to(dev), in_coff, cin, arena.ptr("c"), kc, cout, out, 32, **kw)
+    torch.cuda.synchronize()
+    xin = x[..., in_coff:in_coff + cin].float().permute(0, 3, 1, 2)
+    y = F.conv2d(xin, wgt.to(torch.bfloat16).float(), bias, padding=1)
+    y = torch.where(y > 0, y, y * lrelu)
+    if mask:
+        y = y * torch.where(side[0][..., 32:].float().permute(0, 3, 1, 2) > 0, 1.0, 0.2)
+    if r1:
+        y = 0.2 * y + side[1][..., :cout].float().permute(0, 3, 1, 2)
+    if r2:
+        y = y + 0.5 * side[2][..., 32:].float().permute(0, 3, 1, 2)
+    assert torch.all(out[..., :32] == 3.0)  # channels outside the window untouched
+    got = out[..., 32:].float().permute(0, 3, 1, 2).cpu()
+    return got, y, (cs.cpu() if colsum else None), 0.2 * y.sum(dim=(0, 2, 3))
+
+
+@pytest.mark.parametrize("b,h,w,cin,in_coff,in_ctot,kc,cout,kw", [
+    (1, 16, 8, 32, 0, 32, 32, 32, dict(lrelu=0.2)),                        # one column, one row per band
+    (2, 48, 40, 96, 32, 160, 32, 32, dict(lrelu=0.2)),                     # channel window, 3 K chunks
+    (3, 96, 21, 160, 0, 160, 32, 32, dict(r1=True)),                       # ragged width; conv5 of a dense block
+    (1, 40, 24, 64, 0, 64, 32, 32, dict(r1=True, r2=True)),                # 10 bands of 4 rows; RRDB-end conv5
+    (2, 80, 19, 128, 32, 160, 32, 32, dict(mask=True, colsum=True)),       # data gradient + fused bias gradient
+    (2, 80, 19, 160, 0, 160, 32, 32, dict(r1=True, r2=True, colsum=True)),
+    (1, 144, 30, 32, 0, 32, 32, 32, dict(colsum=True)),
+    (2, 64, 32, 128, 64, 320, 64, 64, dict(lrelu=0.2)),                    # 64 filters: SWIZZLE_128B, 8 accumulator slots
+    (1, 48, 16, 64, 0, 64, 64, 64, dict(mask=True)),
+    (3, 416, 832, 32, 0, 32, 32, 32, dict(lrelu=0.2)),                     # 312 columns: round-robin rounds + tail ranges
+    (1, 416, 416, 64, 0, 64, 32, 32, dict()),                              # batch 1: every CTA a partial column
+])
+def test_conv3x3_row_hop_matches_torch_conv2d(dev, b, h, w, cin, in_coff, in_ctot, kc, cout, kw):
+    """csrc/conv3x3_row.cuh (tap_mode 9: error instead of another kernel if the shape did not qualify) against
+    F.conv2d on bf16-rounded operands: rrdb_blocks.py:37-54 layer shapes, every epilogue flavour the engine uses."""
+    got, want, cs, cs_want = _row_case(dev, b, h, w, cin, in_coff, in_ctot, kc, cout, **kw)
+    assert rel_l2(got, want) < 4e-3  # bf16 output rounding only
+    if cs is not None:
+        assert rel_l2(cs, cs_want) < 2e-2  # sums of bf16-rounded outputs
+
+
+def test_conv3x3_row_hop_is_the_default_where_it_qualifies_and_batch_invariant(dev):
+    """tap_mode 0 with a row-hop weight image takes the row-hop form for H = 416 (bit-equal to tap_mode 9) and not for
+    H = 37 (no divisor in 8..16: the other kernels, same values within rounding); an image computed alone has the
+    same bits as inside a batch (different work splits: partial columns vs whole columns)."""
+    from xmm_superres_denoise_b200 import ops
+    from xmm_superres_denoise_b200.engine import WeightArena, _Blob, _Segment
+
+    g = torch.Generator().manual_seed(5)
+    cin = cout = kc = 32
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(dev)
+    arena = WeightArena()
+    arena.add(_Blob("c", cout, kc, 1, [_Segment(wgt, cin, 0, 0, 0, 0, cin, 1.0)], None))
+    arena.add(_Blob("c.row", cout, kc, 1, [_Segment(wgt, cin, 0, 0, 0, 0, cin, 1.0)], None, tap_order=1))
+    arena.ensure(dev)
+
+    def run(x, tap_mode):
+        out = torch.zeros(x.shape[0], x.shape[1], x.shape[2], cout, dtype=torch.bfloat16, device=dev)
+        ops.conv3x3(x, 0, cin, arena.ptr("c"), kc, cout, out, 0, lrelu=0.2, tap_mode=tap_mode, wblob_row=arena.ptr("c.row"))
+        torch.cuda.synchronize()
+        return out
+
+    x = torch.randn(8, 416, 416, cin, generator=g).to(torch.bfloat16).to(dev)
+    auto, forced, scatter = run(x, 0), run(x, 9), run(x, 4)
+    assert torch.equal(auto, forced)
+    assert rel_l2(auto.float().cpu(), scatter.float().cpu()) < 4e-3
+    alone = run(x[5:6].contiguous(), 0)
+    assert torch.equal(alone[0], auto[5])
+    x37 = x[:2, :37].contiguous()
+    assert rel_l2(run(x37, 0).float().cpu(), run(x37, 4).float().cpu()) < 4e-3
+    with pytest.raises(RuntimeError, match="row-hop"):
+        run(x37, 9)
+
+
 def test_conv3x3_rejects_bad_arguments(dev):
     from xmm_superres_denoise_b200 import ops
 

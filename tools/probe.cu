@@ -185,6 +185,15 @@ static double run_conv_case(const ConvCase& c, int tap_mode, bool verbose) {
     printf("pack failed: %s\n", xmm_last_error());
     exit(2);
   }
+  void* blob_row = nullptr;  // the same layer in the row-hop kernel's block order
+  if (!c.shuffle && c.cout == c.kc) {
+    CK(cudaMalloc(&blob_row, xmm_pack_blob_bytes(c.cout, c.kc, nchunks)));
+    xmm_pack_job job2 = job;
+    job2.dst = blob_row;
+    job2.tap_order = 1;
+    CK(cudaMemcpy(job_d, &job2, sizeof(job2), cudaMemcpyHostToDevice));
+    if (xmm_pack_weights(job_d, 1, nullptr) != 0) { printf("pack (row) failed: %s\n", xmm_last_error()); exit(2); }
+  }
 
   xmm_conv3x3_params p{};
   p.in = in_d; p.in_ctot = c.in_ctot; p.in_coff = c.in_coff; p.cin = c.cin;
@@ -198,6 +207,7 @@ static double run_conv_case(const ConvCase& c, int tap_mode, bool verbose) {
   p.out = out_d; p.out_ctot = c.out_ctot; p.out_coff = c.out_coff;
   p.pixel_shuffle = c.shuffle ? 1 : 0;
   p.tap_mode = tap_mode;
+  p.wblob_row = blob_row;
   int rc = xmm_conv3x3_bf16(&p, nullptr);
   if (rc != 0) {
     printf("conv launch failed rc=%d: %s\n", rc, xmm_last_error());
@@ -260,7 +270,7 @@ static double run_conv_case(const ConvCase& c, int tap_mode, bool verbose) {
            c.B, c.H, c.W, c.cin, c.in_coff, c.in_ctot, c.kc, c.cout, tap_mode, c.bias, c.mask, c.r1, c.r2, c.shuffle,
            max_err, max_ref, max_err / max_ref, bad_untouched, (max_err / max_ref < 2e-2 && bad_untouched == 0) ? "OK" : "FAIL");
   cudaFree(in_d); cudaFree(w_d); cudaFree(b_d); cudaFree(mask_d); cudaFree(r1_d); cudaFree(r2_d); cudaFree(out_d);
-  cudaFree(blob); cudaFree(job_d);
+  cudaFree(blob); cudaFree(job_d); if (blob_row) cudaFree(blob_row);
   return bad_untouched ? 1e9 : max_err / max_ref;
 }
 
@@ -291,7 +301,15 @@ static void time_conv(int B, int H, int W, int F, int k, int kc, int tap_mode, i
   CK(cudaMalloc(&job_d, sizeof(job)));
   CK(cudaMemcpy(job_d, &job, sizeof(job), cudaMemcpyHostToDevice));
   xmm_pack_weights(job_d, 1, nullptr);
+  void* blob_row = nullptr;
+  if (!shuffle && cout == kc) {
+    CK(cudaMalloc(&blob_row, xmm_pack_blob_bytes(cout, kc, nchunks)));
+    job.dst = blob_row; job.tap_order = 1;
+    CK(cudaMemcpy(job_d, &job, sizeof(job), cudaMemcpyHostToDevice));
+    xmm_pack_weights(job_d, 1, nullptr);
+  }
   xmm_conv3x3_params p{};
+  p.wblob_row = blob_row;
   p.in = in_d; p.in_ctot = ctot; p.in_coff = 0; p.cin = cin; p.wblob = blob; p.kc = kc; p.cout = cout;
   p.batch = B; p.height = H; p.width = W; p.lrelu_slope = 0.2f; p.s0 = 1.f;
   p.out = out_d; p.out_ctot = shuffle ? F : ctot; p.out_coff = (shuffle || k == 5) ? 0 : k * F;
@@ -312,6 +330,7 @@ static void time_conv(int B, int H, int W, int F, int k, int kc, int tap_mode, i
   printf("  time conv B%d %dx%d F=%d k=%d cin=%d cout=%d kc=%d mode=%d : %.3f ms  %.1f TFLOP/s (%.1f%% of 1667.8)\n", B, H,
          W, F, k, cin, cout, kc, tap_mode, best, flop / best * 1e-9, 100.0 * flop / best * 1e-9 / 1667.8);
   cudaFree(in_d); if (out_d != in_d) cudaFree(out_d); cudaFree(w_d); cudaFree(blob); cudaFree(job_d);
+  if (blob_row) cudaFree(blob_row);
 }
 
 // ------------------------------------------------------------------ dense-block chain: pipelined vs layer by layer
@@ -429,6 +448,7 @@ int main(int argc, char** argv) {
     run_rate<96, false>(2); run_rate<128, false>(2); run_rate<256, false>(2);
     run_rate<32, true>(2); run_rate<64, true>(2); run_rate<128, true>(2);
     run_rate<32, false, 1>(2); run_rate<32, false, 2>(2); run_rate<64, false, 1>(2); run_rate<64, false, 2>(2);
+    run_rate<96, false, 1>(2); run_rate<96, false, 2>(2); run_rate<96, false, 2>(1);
   }
   int good_mode[2] = {0, 0};  // per kc
   if (do_conv) {
@@ -463,6 +483,35 @@ int main(int argc, char** argv) {
     run_conv_case(e5, m64, true);
   } else {
     good_mode[0] = good_mode[1] = 1;
+  }
+  if (argc >= 2 && strstr(argv[1], "row")) {  // row-hop form (tap_mode 9): correctness, then timing against 4 / 1
+    const int m = 9;
+    ConvCase r0{1, 16, 8, 32, 0, 32, 32, 32, 32, 0, true, false, false, false, false, 0.2f};
+    run_conv_case(r0, m, true);   // one column, one row per band
+    ConvCase r1{2, 48, 40, 160, 32, 96, 32, 32, 160, 128, true, false, false, false, false, 0.2f};
+    run_conv_case(r1, m, true);   // channel windows, 3 chunks
+    ConvCase r2{3, 96, 21, 160, 0, 160, 32, 32, 160, 0, true, false, false, false, false, 1.0f};
+    run_conv_case(r2, m, true);   // ragged width, 5 chunks
+    ConvCase r3{1, 40, 24, 64, 0, 64, 32, 32, 32, 0, true, false, true, true, false, 1.0f};
+    run_conv_case(r3, m, true);   // 10 bands; two residuals
+    ConvCase r4{2, 80, 19, 160, 32, 128, 32, 32, 160, 0, false, true, false, false, false, 1.0f};
+    run_conv_case(r4, m, true);   // LeakyReLU' mask
+    ConvCase r5{2, 64, 32, 64, 0, 64, 64, 64, 64, 0, true, false, true, false, false, 1.0f};
+    run_conv_case(r5, m, true);   // 64 filters (SWIZZLE_128B, 8 slots)
+    ConvCase r6{3, 416, 832, 32, 0, 32, 32, 32, 160, 0, true, false, false, false, false, 0.2f};
+    run_conv_case(r6, m, true);   // 312 columns: round-robin rounds + tail ranges
+    ConvCase r7{1, 416, 416, 64, 0, 64, 32, 32, 64, 32, true, false, false, false, false, 0.2f};
+    run_conv_case(r7, m, true);   // batch 1: every CTA a partial column
+    for (int B : {16, 64}) {
+      for (int mode : {9, 4, 1}) {
+        for (int k = 1; k <= 5; ++k) time_conv(B, 416, 416, 32, k, 32, mode);
+      }
+    }
+    for (int mode : {9, 1})
+      for (int k = 1; k <= 2; ++k) time_conv(8, 416, 416, 64, k, 64, mode);
+    time_conv(1, 416, 416, 32, 2, 32, 9); time_conv(1, 416, 416, 32, 2, 32, 4);
+    time_conv(16, 832, 832, 32, 1, 32, 9); time_conv(16, 832, 832, 32, 1, 32, 1);
+    return 0;
   }
   if (argc >= 2 && strstr(argv[1], "sweep")) {  // timing only (env sweeps of XMM_CHAIN_SPLIT / XMM_CHAIN_SEGS)
     run_chain_case(argc > 2 ? atoi(argv[2]) : 16, 416, 416, true);

@@ -23,7 +23,8 @@ class PackSegment(Structure):
 
 class PackJob(Structure):
     _fields_ = [("dst", c_void_p), ("bias", c_void_p), ("nt", c_int), ("kc", c_int), ("nchunks", c_int),
-                ("nseg", c_int), ("perm", c_int), ("n_valid", c_int), ("bias_n", c_int), ("seg", PackSegment * 5)]
+                ("nseg", c_int), ("perm", c_int), ("n_valid", c_int), ("bias_n", c_int), ("seg", PackSegment * 5),
+                ("tap_order", c_int)]
 
 
 class Conv3x3Params(Structure):
@@ -37,7 +38,7 @@ class Conv3x3Params(Structure):
                 ("r2", c_void_p), ("r2_ctot", c_int), ("r2_coff", c_int), ("s2", c_float),
                 ("out", c_void_p), ("out_ctot", c_int), ("out_coff", c_int),
                 ("pixel_shuffle", c_int), ("tap_mode", c_int), ("colsum", c_void_p), ("colsum_scale", c_float),
-                ("shuffle_stride", c_int)]
+                ("shuffle_stride", c_int), ("wblob_row", c_void_p)]
 
 
 class NormalizeParams(Structure):

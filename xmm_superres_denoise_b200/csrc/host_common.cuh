@@ -136,4 +136,34 @@ inline int make_nhwc_tmap(CUtensorMap* out, const void* base, int batch, int hei
   return XMM_OK;
 }
 
+// The same NHWC buffer viewed as nbands horizontal bands of band_h rows (height == nbands * band_h): a 5-D tensor
+// (c, x, row-in-band, band, b).  A box is (box_c channels) x (box_w pixels) of ONE row-in-band of box_bands
+// consecutive bands -- the M = [bands][pixels] tile of the row-hop conv (conv3x3_row.cuh).  Bands / pixels outside
+// the tensor are zero-filled on loads and clipped on stores.
+inline int make_band_tmap(CUtensorMap* out, const void* base, int batch, int height, int width, int ctot, int band_h,
+                          int nbands, int box_c, int box_w, int box_bands) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(XMM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (band_h * nbands != height) return fail(XMM_ERR_INVALID_ARGUMENT, "band view: %d x %d != height %d", nbands, band_h, height);
+  cuuint64_t dims[5] = {cuuint64_t(ctot), cuuint64_t(width), cuuint64_t(band_h), cuuint64_t(nbands), cuuint64_t(batch)};
+  cuuint64_t strides[4] = {cuuint64_t(ctot) * 2, cuuint64_t(ctot) * 2 * width, cuuint64_t(ctot) * 2 * width * band_h,
+                           cuuint64_t(ctot) * 2 * width * height};
+  cuuint32_t box[5] = {cuuint32_t(box_c), cuuint32_t(box_w), 1, cuuint32_t(box_bands), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (box_c * 2 == 128)
+    sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (box_c * 2 == 64)
+    sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (box_c * 2 == 32)
+    sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMapL2promotion promo = box_c * 2 <= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(XMM_ERR_CUDA, "cuTensorMapEncodeTiled (band view) failed (%d) for [%d,%d,%d,%d] bands %dx%d box [%d,%d,%d]",
+                int(r), batch, height, width, ctot, nbands, band_h, box_c, box_w, box_bands);
+  return XMM_OK;
+}
+
 }  // namespace xmm

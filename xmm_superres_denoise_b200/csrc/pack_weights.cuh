@@ -1,7 +1,8 @@
 // Repack fp32 OIHW convolution weights (the nn.Conv2d parameters the reference keeps,
 // generator_rrdb.py:31-54, rrdb_blocks.py:27-31) into the bf16 shared-memory image the
 // tensor-core kernel bulk-copies: [chunk][tap][n][k] with the UMMA K-major 64B/128B
-// swizzle already applied, followed by NT fp32 biases.
+// swizzle already applied, followed by NT fp32 biases.  The tap blocks come in one of two orders
+// (xmm_pack_job::tap_order): dy*3+dx, or dx*3+(2-dy) for the row-hop kernel (conv3x3_row.cuh).
 //
 // One launch repacks every layer of the model: jobs live in a device-side table that is
 // built once (parameter storage is stable across optimizer steps).
@@ -21,7 +22,11 @@ __global__ void pack_jobs_kernel(const xmm_pack_job* __restrict__ jobs) {
   uint8_t* dst = static_cast<uint8_t*>(job.dst);
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int ch = blk / 9, tap = blk - ch * 9;
-    const int dy = tap / 3, dx = tap - dy * 3;
+    int dy = tap / 3, dx = tap - dy * 3;
+    if (job.tap_order == 1) {  // row-hop order: block = dx * 3 + (2 - dy)
+      dx = tap / 3;
+      dy = 2 - (tap - dx * 3);
+    }
     uint8_t* bdst = dst + size_t(blk) * job.nt * rowb;
     for (int e = threadIdx.x; e < job.nt * job.kc; e += blockDim.x) {
       const int n = e / job.kc, k = e - n * job.kc;

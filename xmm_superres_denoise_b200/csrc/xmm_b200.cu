@@ -6,6 +6,7 @@
 
 #include "conv3x3_chain.cuh"
 #include "conv3x3_dx.cuh"
+#include "conv3x3_row.cuh"
 #include "conv3x3_tc.cuh"
 #include "edge_kernels.cuh"
 #include "host_common.cuh"
@@ -61,6 +62,22 @@ struct TmapKeyHash {
     return h;
   }
 };
+
+
+// cudaFuncSetAttribute is per DEVICE: remember (kernel, device) pairs, not just kernels (a second GPU driven from
+// the same process would otherwise never get the > 48 KB dynamic shared-memory opt-in).
+int ensure_max_smem(const void* kernel, const DeviceInfo& dev, int reserve = 0) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, unsigned long long> done;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    unsigned long long& bits = done[kernel];
+    if (bits & (1ull << dev.device)) return XMM_OK;
+    bits |= 1ull << dev.device;
+  }
+  XMM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin - reserve));
+  return XMM_OK;
+}
 
 // Descriptors are pure functions of (pointer, shape); caching only saves the encode call.
 int cached_tmap(CUtensorMap* out, const void* base, int batch, int height, int width, int ctot, int box_c,
@@ -153,12 +170,8 @@ int launch_conv_impl(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStr
     if (rc != XMM_OK) return rc;
   }
 
-  static bool attr_set = false;  // per instantiation; benign race (idempotent call)
-  if (!attr_set) {
-    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_tc_kernel<KC, NT, MODE, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dev.max_smem_optin));
-    attr_set = true;
-  }
+  rc = ensure_max_smem(reinterpret_cast<const void*>(conv3x3_tc_kernel<KC, NT, MODE, EG>), dev);
+  if (rc != XMM_OK) return rc;
   const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
   conv3x3_tc_kernel<KC, NT, MODE, EG><<<grid, Cfg::kThreads, smem, stream>>>(tmap, tmap_out, a);
   XMM_CUDA_OK(cudaGetLastError());
@@ -232,12 +245,8 @@ int launch_conv_dx_impl(const xmm_conv3x3_params& p, const DeviceInfo& dev, cuda
       if (rc != XMM_OK) return rc;
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT, false, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dev.max_smem_optin));
-    attr_set = true;
-  }
+  rc = ensure_max_smem(reinterpret_cast<const void*>(conv3x3_dx_kernel<KC, NT, false, G2>), dev);
+  if (rc != XMM_OK) return rc;
   const int grid = a.num_tiles < dev.sm_count ? a.num_tiles : dev.sm_count;
   // >= 4 strips per CTA: deal whole strips round-robin (halo rows of adjacent strips meet in L2); XMM_DX_RR=0/1 forces
   static const int rr_env = [] { const char* e = getenv("XMM_DX_RR"); return e ? atoi(e) : -1; }();
@@ -251,12 +260,8 @@ int launch_conv_dx_impl(const xmm_conv3x3_params& p, const DeviceInfo& dev, cuda
   if constexpr (!G2)
   if (KC == 32 && NT == 32 && (pair_env || p.tap_mode == 6) && p.tap_mode != 5 && a.strip_rr && grid % 2 == 0 &&
       nstrips >= grid) {
-    static bool pair_attr_set = false;
-    if (!pair_attr_set) {
-      XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_dx_kernel<KC, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       dev.max_smem_optin));
-      pair_attr_set = true;
-    }
+    rc = ensure_max_smem(reinterpret_cast<const void*>(conv3x3_dx_kernel<KC, NT, true>), dev);
+    if (rc != XMM_OK) return rc;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(grid));
     cfg.blockDim = dim3(kDxThreads);
@@ -299,6 +304,162 @@ int launch_conv_dx(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStrea
       return launch_conv_dx_impl<KC, NT, true>(p, dev, stream);
   }
   return launch_conv_dx_impl<KC, NT, false>(p, dev, stream);
+}
+
+
+// ----------------------------------------------------------------------------- row-hop form (conv3x3_row.cuh)
+struct BandTmapKey {
+  const void* base;
+  int batch, height, width, ctot, band_h, nbands, box_c, box_w, box_bands;
+  bool operator==(const BandTmapKey& o) const {
+    return base == o.base && batch == o.batch && height == o.height && width == o.width && ctot == o.ctot &&
+           band_h == o.band_h && nbands == o.nbands && box_c == o.box_c && box_w == o.box_w && box_bands == o.box_bands;
+  }
+};
+struct BandTmapKeyHash {
+  size_t operator()(const BandTmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.batch); mix(k.height); mix(k.width); mix(k.ctot); mix(k.band_h); mix(k.nbands); mix(k.box_c); mix(k.box_w);
+    mix(k.box_bands);
+    return h;
+  }
+};
+int cached_band_tmap(CUtensorMap* out, const void* base, int batch, int height, int width, int ctot, int band_h,
+                     int nbands, int box_c, int box_w, int box_bands) {
+  static std::mutex mu;
+  static std::unordered_map<BandTmapKey, CUtensorMap, BandTmapKeyHash> cache;
+  BandTmapKey key{base, batch, height, width, ctot, band_h, nbands, box_c, box_w, box_bands};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return XMM_OK;
+  }
+  int rc = make_band_tmap(out, base, batch, height, width, ctot, band_h, nbands, box_c, box_w, box_bands);
+  if (rc != XMM_OK) return rc;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return XMM_OK;
+}
+
+// height = nbands * band_h with the largest nbands <= 16 (lanes of missing bands idle: at least half must work)
+bool row_bands(int height, int* nbands, int* band_h) {
+  for (int n = kRowBands; n >= kRowBands / 2; --n)
+    if (height % n == 0) {
+      *nbands = n;
+      *band_h = height / n;
+      return true;
+    }
+  return false;
+}
+
+int row_epi_flags(const xmm_conv3x3_params& p) {
+  return (p.lrelu_slope != 1.0f ? kRowLrelu : 0) | (p.mask ? kRowMask : 0) | (p.r1 ? kRowR1 : 0) | (p.r2 ? kRowR2 : 0) |
+         (p.colsum ? kRowCsum : 0);
+}
+bool row_epi_built(int f) {
+  switch (f) {
+    case 0: case kRowLrelu: case kRowR1: case kRowR1 | kRowR2: case kRowMask: case kRowMask | kRowCsum: case kRowCsum:
+    case kRowR1 | kRowCsum: case kRowR1 | kRowR2 | kRowCsum:
+      return true;
+    default:
+      return false;
+  }
+}
+
+// Why (if at all) this launch cannot take the row-hop form; nullptr = it can.  stages_out: activation stages.
+template <int KC, int NT>
+const char* row_blocker(const xmm_conv3x3_params& p, const DeviceInfo& dev, int* stages_out) {
+  using Cfg = RowCfg<KC, NT>;
+  if (p.wblob_row == nullptr) return "no row-hop weight image (wblob_row)";
+  if (p.pixel_shuffle != 0) return "pixel shuffle";
+  int nbands, band_h;
+  if (!row_bands(p.height, &nbands, &band_h)) return "height has no divisor in 8..16";
+  const int flags = row_epi_flags(p);
+  if (!row_epi_built(flags)) return "epilogue combination not instantiated";
+  if ((flags & kRowCsum) && NT != 32) return "fused column sums need cout = 32";
+  const int nside = (p.mask != nullptr) + (p.r1 != nullptr) + (p.r2 != nullptr);
+  const uint32_t w_bytes = uint32_t(p.cin / KC) * 9u * Cfg::kTapBytes;
+  const size_t fixed = Cfg::smem_bytes(w_bytes, 0, nside);
+  if (fixed + 3 * size_t(Cfg::kStageBytes) > size_t(dev.max_smem_optin)) return "weights do not fit next to 3 pipeline stages";
+  int stages = int((size_t(dev.max_smem_optin) - fixed) / Cfg::kStageBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  *stages_out = stages;
+  return nullptr;
+}
+
+template <int KC, int NT, int EPI>
+int launch_conv_row_epi(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream, int stages) {
+  using Cfg = RowCfg<KC, NT>;
+  RowArgs a{};
+  a.wblob = p.wblob_row;
+  a.nchunks = p.cin / KC;
+  a.w_bytes = uint32_t(a.nchunks) * 9u * Cfg::kTapBytes;
+  a.cin_off = p.in_coff;
+  a.batch = p.batch;
+  a.height = p.height;
+  a.width = p.width;
+  row_bands(p.height, &a.nbands, &a.band_h);
+  a.tiles_x = (p.width + kRowPx - 1) / kRowPx;
+  a.ncols = a.tiles_x * p.batch;
+  a.stages = stages;
+  const void* side_ptr[3] = {p.mask, p.r1, p.r2};
+  const int side_ctot[3] = {p.mask_ctot, p.r1_ctot, p.r2_ctot};
+  int nside = 0;
+  for (int k = 0; k < 3; ++k)
+    if (side_ptr[k] != nullptr) { a.side_mask |= 1 << k; ++nside; }
+  fill_epilogue(a.epi, p);
+  const long long total_rows = (long long)a.ncols * a.band_h;
+  const int grid = total_rows < dev.sm_count ? int(total_rows) : dev.sm_count;
+  // whole columns round-robin while they fill rounds (neighbouring columns run side by side: shared halo pixels meet
+  // in L2), the rest as equal row ranges; XMM_ROW_RR=0 forces contiguous ranges only (experiments)
+  static const int rr_env = [] { const char* e = getenv("XMM_ROW_RR"); return e ? atoi(e) : 1; }();
+  a.rr_rounds = (rr_env && a.ncols >= 2 * grid) ? a.ncols / grid : 0;
+  CUtensorMap tmap, tmap_out;
+  int rc = cached_band_tmap(&tmap, p.in, p.batch, p.height, p.width, p.in_ctot, a.band_h, a.nbands, KC, kRowPitch, kRowBands);
+  if (rc != XMM_OK) return rc;
+  rc = cached_band_tmap(&tmap_out, p.out, p.batch, p.height, p.width, p.out_ctot, a.band_h, a.nbands, NT, kRowPx, 4);
+  if (rc != XMM_OK) return rc;
+  RowSideMaps sides;
+  for (int k = 0; k < 3; ++k) {
+    sides.m[k] = tmap;
+    if (a.side_mask & (1 << k)) {
+      rc = cached_band_tmap(&sides.m[k], side_ptr[k], p.batch, p.height, p.width, side_ctot[k], a.band_h, a.nbands, NT,
+                            kRowPx, kRowBands);
+      if (rc != XMM_OK) return rc;
+    }
+  }
+  rc = ensure_max_smem(reinterpret_cast<const void*>(conv3x3_row_kernel<KC, NT, EPI>), dev);
+  if (rc != XMM_OK) return rc;
+  const size_t smem = Cfg::smem_bytes(a.w_bytes, stages, nside);
+  conv3x3_row_kernel<KC, NT, EPI><<<grid, kRowThreads, smem, stream>>>(tmap, tmap_out, sides, a);
+  XMM_CUDA_OK(cudaGetLastError());
+  return XMM_OK;
+}
+
+template <int KC, int NT>
+int launch_conv_row(const xmm_conv3x3_params& p, const DeviceInfo& dev, cudaStream_t stream, int stages) {
+  switch (row_epi_flags(p)) {
+#define XMM_ROW_CASE(F_) case (F_): return launch_conv_row_epi<KC, NT, (F_)>(p, dev, stream, stages);
+    XMM_ROW_CASE(0)
+    XMM_ROW_CASE(kRowLrelu)
+    XMM_ROW_CASE(kRowR1)
+    XMM_ROW_CASE(kRowR1 | kRowR2)
+    XMM_ROW_CASE(kRowMask)
+    default: break;
+  }
+  if constexpr (NT == 32) {
+    switch (row_epi_flags(p)) {
+      XMM_ROW_CASE(kRowCsum)
+      XMM_ROW_CASE(kRowMask | kRowCsum)
+      XMM_ROW_CASE(kRowR1 | kRowCsum)
+      XMM_ROW_CASE(kRowR1 | kRowR2 | kRowCsum)
+#undef XMM_ROW_CASE
+      default: break;
+    }
+  }
+  return fail(XMM_ERR_INVALID_ARGUMENT, "conv3x3 (row-hop): epilogue combination %d is not instantiated", row_epi_flags(p));
 }
 
 template <int KC, int NT>
@@ -353,6 +514,21 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   rc = check_conv_params(p);
   if (rc != XMM_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Row-hop form (conv3x3_row.cuh): the default wherever it qualifies (tap_mode 0 with a row-hop weight image);
+  // tap_mode 9 forces it; XMM_ROW=0 switches it off (A/B runs).
+  static const int row_env = [] { const char* e = getenv("XMM_ROW"); return e ? atoi(e) : 1; }();
+  if ((p.tap_mode <= 0 && row_env && p.wblob_row != nullptr) || p.tap_mode == 9) {
+    const char* why = "cout must equal kc (32 or 64)";
+    int stages = 0;
+    if (p.kc == 32 && p.cout == 32) {
+      why = row_blocker<32, 32>(p, dev, &stages);
+      if (why == nullptr) return launch_conv_row<32, 32>(p, dev, s, stages);
+    } else if (p.kc == 64 && p.cout == 64) {
+      why = row_blocker<64, 64>(p, dev, &stages);
+      if (why == nullptr) return launch_conv_row<64, 64>(p, dev, s, stages);
+    }
+    if (p.tap_mode == 9) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3: the row-hop form does not qualify (%s)", why);
+  }
   // tap_mode 0 = auto: the column-scatter form (conv3x3_dx.cuh) wherever it is faster than the haloed tap views
   // (measured on B200, 16x416x416, F=32: cin 64..160 -> 1.13x..1.37x; cin = 32 ties; F=64 layers are faster on the
   // tap views, whose N=64 MMAs are less shared-memory bound).  4 forces it.
@@ -497,11 +673,9 @@ int launch_chain(const xmm_conv3x3_params* L, int n, const DeviceInfo& dev, int*
   }
   const int total_ctas = begin;
   XMM_CUDA_OK(cudaMemsetAsync(done, 0, size_t(n) * nstrips * sizeof(int), stream));
-  static bool attr_set = false;
-  if (!attr_set) {
-    XMM_CUDA_OK(cudaFuncSetAttribute(conv3x3_chain_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dev.max_smem_optin));
-    attr_set = true;
+  {
+    const int rc_attr = ensure_max_smem(reinterpret_cast<const void*>(conv3x3_chain_kernel<32, 32>), dev);
+    if (rc_attr != XMM_OK) return rc_attr;
   }
   // XMM_CHAIN_PROF=1 (developer): per-layer-group cycle counters of this launch, printed after a device sync
   static const bool prof_on = env_int("XMM_CHAIN_PROF", 0) != 0;
@@ -873,12 +1047,8 @@ extern "C" int xmm_conv3x3_wgrad(const xmm_wgrad_params* pp, void* stream) {
   if (rc != XMM_OK) return rc;
   rc = cached_tmap(&ty, p.dy, p.batch, p.height, p.width, p.dy_ctot, 64, kTileW, kWgTileH);
   if (rc != XMM_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XMM_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     dev.max_smem_optin - 1024));  // the kernel also has static shared memory
-    attr_set = true;
-  }
+  rc = ensure_max_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), dev, 1024);  // the kernel also has static shared memory
+  if (rc != XMM_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   wgrad_tc_kernel<<<dev.sm_count, kWgThreads, smem, s>>>(tx, ty, tx32, tx8, a);
   XMM_CUDA_OK(cudaGetLastError());

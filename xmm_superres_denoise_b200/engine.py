@@ -57,6 +57,7 @@ class _Blob:
     perm: int = 0
     bias_n: int = -1  # rows that take a bias (-1: all)
     offset: int = 0  # byte offset inside the blob arena
+    tap_order: int = 0  # 1: the row-hop kernel's block order dx*3 + (2 - dy) (xmm_pack_job.tap_order)
 
     @property
     def nbytes(self) -> int:
@@ -112,6 +113,7 @@ class WeightArena:
                 j.bias = b.bias.data_ptr() if b.bias is not None else None
                 j.nt, j.kc, j.nchunks, j.nseg, j.perm, j.n_valid = b.nt, b.kc, b.nchunks, len(b.segments), b.perm, b.nt
                 j.bias_n = b.nt if b.bias_n < 0 else b.bias_n
+                j.tap_order = b.tap_order
                 if len(b.segments) > 5:
                     raise RuntimeError(f"{b.name}: a packed layer takes at most 5 source segments")
                 for s_c, s in zip(j.seg, b.segments):
@@ -148,7 +150,7 @@ class _LayerPlans:
         cout, cin = conv.weight.shape[0], conv.weight.shape[1]
         if 9 * cin * cout * 2 <= _WEIGHT_BUDGET:
             self.arena.add(_fwd_blob(name, conv, self.kc, perm))
-            self.plans[name] = [(name, self.kc, cout, 0)]
+            self.plans[name] = [(name, self.kc, cout, 0, self._row_twin(_fwd_blob(name, conv, self.kc, perm)))]
             return
         part = 128 if perm else 32
         if cout % part or 9 * cin * part * 2 > 190 * 1024:
@@ -156,10 +158,25 @@ class _LayerPlans:
         plan = []
         for n0 in range(0, cout, part):
             pname = f"{name}.n{n0}"
-            self.arena.add(_Blob(pname, part, 32, cin // 32, [_Segment(conv.weight, cin, n0, 0, 0, 0, cin, 1.0)],
-                                 conv.bias, perm))
-            plan.append((pname, 32, part, n0))
+
+            def mk(pname=pname, n0=n0):
+                return _Blob(pname, part, 32, cin // 32, [_Segment(conv.weight, cin, n0, 0, 0, 0, cin, 1.0)],
+                             conv.bias, perm)
+
+            self.arena.add(mk())
+            plan.append((pname, 32, part, n0, self._row_twin(mk())))
         self.plans[name] = plan
+
+    def _row_twin(self, blob: _Blob) -> Optional[str]:
+        """The same layer packed a second time in the row-hop kernel's block order (``xmm_conv3x3_params.wblob_row``)
+        where that kernel can take it: cout == kc in (32, 64), no pixel-shuffle permutation.  Whether a launch
+        really uses it is decided per call by the library (image height, shared memory)."""
+        if blob.perm or blob.nt != blob.kc or blob.nt not in (32, 64):
+            return None
+        blob.name += ".row"
+        blob.tap_order = 1
+        self.arena.add(blob)
+        return blob.name
 
     def _add_planned(self, name: str, rows: int, k_total: int, make_blob) -> None:
         """A packed layer described by ``make_blob(blob_name, n0, nt, kc) -> _Blob`` (rows [n0, n0+nt) of the layer's
@@ -167,7 +184,7 @@ class _LayerPlans:
         parts of 32 rows with 32-channel K chunks (data-gradient layers of the 64-filter generators)."""
         if 9 * k_total * rows * 2 <= _WEIGHT_BUDGET:
             self.arena.add(make_blob(name, 0, rows, self.kc))
-            self.plans[name] = [(name, self.kc, rows, 0)]
+            self.plans[name] = [(name, self.kc, rows, 0, self._row_twin(make_blob(name, 0, rows, self.kc)))]
             return
         if rows % 32 or 9 * k_total * 32 * 2 > 190 * 1024:
             raise NotImplementedError(f"{name}: a {k_total}->{rows} layer does not fit the resident-weight kernels")
@@ -175,7 +192,7 @@ class _LayerPlans:
         for n0 in range(0, rows, 32):
             pname = f"{name}.n{n0}"
             self.arena.add(make_blob(pname, n0, 32, 32))
-            plan.append((pname, 32, 32, n0))
+            plan.append((pname, 32, 32, n0, self._row_twin(make_blob(pname, n0, 32, 32))))
         self.plans[name] = plan
 
     def _conv(self, name: str, inp: torch.Tensor, in_coff: int, cin: int, out: torch.Tensor, out_coff: int, **kw):
@@ -183,9 +200,11 @@ class _LayerPlans:
         calls = []
         shuffle = kw.get("pixel_shuffle", 0) == 1
         plan = self.plans[name]
-        rows = sum(nt for _, _, nt, _ in plan)
-        for blob, kc, nt, n0 in plan:
+        rows = sum(p[2] for p in plan)
+        for blob, kc, nt, n0, row_blob in plan:
             k2 = dict(kw)
+            if row_blob is not None and k2.get("pixel_shuffle", 0) == 0:
+                k2["wblob_row"] = self.arena.ptr(row_blob)
             for key in ("r1_coff", "r2_coff", "mask_coff"):
                 if key in k2 and k2.get(key[:-5]) is not None:
                     k2[key] = k2[key] + n0
@@ -221,7 +240,7 @@ class RRDBEngine(_LayerPlans):
         self.num_upsample = getattr(gen, "num_upsample", 0)
         self._gen_ref = [gen]  # no nn.Module registration (avoid a reference cycle in the module tree)
         self.arena = WeightArena()
-        self.plans: Dict[str, List[Tuple[str, int, int, int]]] = {}
+        self.plans: Dict[str, List[Tuple[str, int, int, int, Optional[str]]]] = {}
         g = gen
         for i, rrdb in enumerate(g.rrdb):
             for r, rdb in enumerate((rrdb.RDB1, rrdb.RDB2, rrdb.RDB3)):

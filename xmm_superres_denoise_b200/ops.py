@@ -39,12 +39,13 @@ def _conv3x3_params(p: Conv3x3Params, inp: torch.Tensor, in_coff: int, cin: int,
                     r2: Optional[torch.Tensor] = None, r2_coff: int = 0, s2: float = 0.0,
                     mask: Optional[torch.Tensor] = None, mask_coff: int = 0, mask_slope: float = 1.0,
                     pixel_shuffle: int = 0, tap_mode: int = 0, colsum: Optional[torch.Tensor] = None,
-                    colsum_scale: float = 1.0, shuffle_stride: int = 0) -> None:
+                    colsum_scale: float = 1.0, shuffle_stride: int = 0, wblob_row: Optional[int] = None) -> None:
     _nhwc(inp, "conv3x3 input")
     _nhwc(out, "conv3x3 output")
     b, h, w, ctot = inp.shape
     p.in_, p.in_ctot, p.in_coff, p.cin = inp.data_ptr(), ctot, in_coff, cin
     p.wblob, p.kc, p.cout = wblob_ptr, kc, cout
+    p.wblob_row = wblob_row
     p.batch, p.height, p.width = b, h, w
     p.lrelu_slope = lrelu
     if mask is not None:
@@ -80,7 +81,8 @@ def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, 
     """out[..., out_coff:out_coff+cout] = epilogue(conv3x3(inp[..., in_coff:in_coff+cin])).
 
     Keywords: lrelu, s0, r1/r1_coff/s1, r2/r2_coff/s2, mask/mask_coff/mask_slope, pixel_shuffle, tap_mode,
-    colsum/colsum_scale (fused bias gradient: colsum += scale * column sums of the written values).
+    colsum/colsum_scale (fused bias gradient: colsum += scale * column sums of the written values),
+    wblob_row (the layer's row-hop weight image: lets the library pick conv3x3_row.cuh where the shape qualifies).
     See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
     p = Conv3x3Params()
     _conv3x3_params(p, inp, in_coff, cin, wblob_ptr, kc, cout, out, out_coff, **kw)
