@@ -329,6 +329,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default 64 inference / 16 training)")
     ap.add_argument("--no-train-extra", action="store_true", help="skip the short training measurements in `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run check of one output image (F=32 nb=4: ~1 s)")
     ap.add_argument("--filters", type=int, default=NF, help="developer sweeps only (BASELINE's configs are 32 / 4)")
     ap.add_argument("--blocks", type=int, default=NB)
     args = ap.parse_args()
@@ -461,6 +462,23 @@ def main() -> None:
         barrier()
         e2e_ms = max(s2.elapsed_time(t2), (time.perf_counter() - t_wall) * 1e3)  # device events vs host wall: the larger
 
+        # ------------------------------------------------------------ parity self-check (outside every timed region)
+        # One image of the batch the bench just produced -- through the exact dispatch that was timed (batch-64 work
+        # split, pipeline, pinned host buffers) -- against the CPU arm's fp32 forward of the same counts
+        # (models/model.py:48-49: clamp(generator(normalise(x)), 0, 1)).  north_star's bar: rel-L2 <= 1e-2 for bf16.
+        parity = None
+        if rank == 0 and not args.no_parity:
+            idx = 37 % B
+            last_slot = (args.steps + 1) & 1
+            got = out_hosts[last_slot][idx:idx + 1].clone()
+            dev_out = model(x_dev)[idx:idx + 1].float().cpu()  # the device-resident call the `value` loop timed
+            fwd, p_kind, _ = cpu_forward_fn()
+            rate = counts_hosts[last_slot][idx:idx + 1].reshape(1, 1, 416, 416).float() / t_lr
+            want = fwd(rate)
+            parity = {"rel_l2": float((got - want).norm() / want.norm()),
+                      "rel_l2_device_resident": float((dev_out - want).norm() / want.norm()),
+                      "image": idx, "against": p_kind, "tolerance": 1e-2}
+
     train_extra = {}
     if not args.no_train_extra:
         del model, x_dev, counts_dev
@@ -513,11 +531,16 @@ def main() -> None:
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": kind,
                                 "sample": "3 steps x %d images of the same workload (%.1f s), %s" % (
                                     CPU_IMAGES_PER_STEP, dt, desc)}
+    if parity is not None:
+        line["parity_rel_l2"] = parity["rel_l2"]
+        line["parity"] = parity
     if train_extra:
         line["extra"] = train_extra
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and not max(parity["rel_l2"], parity["rel_l2_device_resident"]) <= parity["tolerance"]:
+        raise SystemExit("bench.py: output of the timed dispatch is outside the parity tolerance: %r" % (parity,))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,126 @@
+"""GPU (B200): parity at the sizes -- and therefore through the exact kernel dispatches -- that bench.py times.
+
+The library picks a kernel form and a work split from the problem size (row-hop columns dealt round-robin, tail
+ranges, epilogue groups ...): BASELINE configs[1] (SR-2x inference, batch 64 of 416x416) and configs[2]/[3]
+(training, batch 16 of 416x416) reach dispatches the small-image tests never see.  Here those exact shapes are held
+to the oracle (sampled images: a full CPU forward/backward per image) and to size-independent properties
+(batch invariance bit for bit; the batch gradient is the mean of the per-image gradients)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rrdb_oracle as O
+from oracle.make_golden import LR_MAX
+from oracle.synthetic import count_batch
+
+from helpers import GRAD_REL, REL_L2_BF16, rel_l2
+
+pytestmark = pytest.mark.gpu
+HR_MAX_SR = 0.0005584  # res/baseline_config.toml:42
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from xmm_superres_denoise_b200 import _lib
+
+    _lib.check(_lib.load().xmm_check_device())
+    return torch.device("cuda:0")
+
+
+def _model(kind, sd, dev, train=False):
+    from xmm_superres_denoise_b200.models import GeneratorRRDB_DN, GeneratorRRDB_SR
+
+    m = GeneratorRRDB_DN(1, 1, 32, 4) if kind == "dn" else GeneratorRRDB_SR(1, 1, 32, 4, num_upsample=1)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    return m.train() if train else m.eval()
+
+
+def _batch(n, kind, seed):
+    lr, hr, t_lr, t_hr = count_batch(n, seed=seed, kind=kind)
+    x = O.normalize_image(torch.from_numpy(lr.astype(np.float32) / t_lr), LR_MAX, "sqrt")
+    t = O.normalize_image(torch.from_numpy(hr.astype(np.float32) / t_hr), LR_MAX if kind == "dn" else HR_MAX_SR, "sqrt")
+    return x, t
+
+
+def test_sr_inference_batch64_headline_dispatch(dev):
+    """BASELINE configs[1] as bench.py runs it: F=32 nb=4 SR-2x, batch 64 of 416x416 through the default dispatch.
+    Images 0, 37 and 63 against the fp32 oracle (generator_rrdb.py:103-110, models/model.py:48-49) within 1e-2, and
+    every one of the 64 outputs bit-equal to the same image run alone (batch 1: another work split, CUDA-graph
+    replay)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state_dict("sr", 1, 1, 32, 4, 1, seed=21)
+    x, _ = _batch(64, "sr", seed=11)
+    m = _model("sr", sd, dev)
+    xd = x.to(dev)
+    with torch.no_grad():
+        full = torch.clamp(m(xd), 0, 1)
+        for i in (0, 37, 63):
+            want = O.model_forward(x[i:i + 1], sd, "sr", 1)
+            r = rel_l2(full[i:i + 1].cpu(), want)
+            print(f"batch-64 SR image {i}: rel-L2 vs oracle = {r:.3e}")
+            assert r < REL_L2_BF16
+        for i in range(64):
+            alone = torch.clamp(m(xd[i:i + 1]), 0, 1)
+            assert torch.equal(alone[0], full[i]), f"image {i} differs between batch 64 and batch 1"
+
+
+def _train_step(kind, weights, sd, dev):
+    from xmm_superres_denoise_b200.training import TrainStep
+    from xmm_superres_denoise_b200.utils.loss_functions import create_loss
+
+    return TrainStep(_model(kind, sd, dev, train=True), create_loss(O.sc_dict_for("sqrt"), weights), lr=1e-4)
+
+
+@pytest.mark.parametrize("kind", ["dn", "sr"])
+def test_training_batch16_dispatch_gradient_is_mean_of_per_image_gradients(dev, kind):
+    """BASELINE configs[2]/[3] shape: batch 16 of 416x416 through TrainStep's forward + loss + backward (no optimizer
+    step).  With the per-image-separable terms (L1 is a mean over pixels; the Poisson term is mean / batch size,
+    metrics/metrics.py:36-38, so its per-image weight is w / 16) the batch gradient is the mean of the sixteen
+    batch-1 gradients -- other work splits, other split-K orders -- to 1e-3."""
+    sd = O.init_state_dict(kind, 1, 1, 32, 4, 1, seed=21)
+    x, t = _batch(16, kind, seed=7)
+    xd, td = x.to(dev), t.to(dev)
+    step = _train_step(kind, {"l1": 0.5, "poisson": 0.5}, sd, dev)
+    _, flat = step._fwd_bwd(xd, td)
+    g16 = flat.clone()
+    one = _train_step(kind, {"l1": 0.5, "poisson": 0.5 / 16}, sd, dev)
+    acc = torch.zeros_like(g16, dtype=torch.float64)
+    for i in range(16):
+        _, fi = one._fwd_bwd(xd[i:i + 1], td[i:i + 1])
+        acc += fi.double()
+    r = rel_l2(g16, (acc / 16).float())
+    print(f"{kind}: batch-16 gradient vs mean of per-image gradients: rel-L2 = {r:.3e}")
+    assert r < 1e-3
+
+
+@pytest.mark.parametrize("kind,weights", [("dn", {"l1": 0.5, "poisson": 0.5}),
+                                          ("sr", {"l1": 0.3, "poisson": 0.3, "ms_ssim": 0.4})])
+def test_training_batch16_dispatch_loss_and_gradient_vs_oracle(dev, kind, weights):
+    """The bench's training losses (create_loss, utils/loss_functions.py:11-47) at 416x416: the loss of a 2-image
+    sub-batch against the oracle's fp32 forward + composite loss, and ONE full-size image's whole gradient vector
+    against the oracle's autograd (models/model.py:51-70: loss(preds=clamp(generator(lr)), target=hr))."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state_dict(kind, 1, 1, 32, 4, 1, seed=21)
+    x, t = _batch(16, kind, seed=7)
+    xd, td = x.to(dev), t.to(dev)
+    step = _train_step(kind, weights, sd, dev)
+    st16, _ = step._fwd_bwd(xd, td)  # the batch-16 dispatch itself runs (and its loss is finite)
+    assert np.isfinite(float(st16["total"]))
+    st2, _ = step._fwd_bwd(xd[:2], td[:2])
+    with torch.no_grad():
+        want2 = O.composite_loss(O.model_forward(x[:2], sd, kind, 1), t[:2], weights, O.sc_dict_for("sqrt"))
+    print(f"{kind}: 2-image loss {float(st2['total']):.6f} vs oracle {float(want2):.6f}")
+    assert abs(float(st2["total"]) - float(want2)) <= GRAD_REL * abs(float(want2))
+
+    _, flat = step._fwd_bwd(xd[3:4], td[3:4])
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss = O.composite_loss(O.model_forward(x[3:4], sdg, kind, 1), t[3:4], weights, O.sc_dict_for("sqrt"))
+    loss.backward()
+    names = [n for n, _ in step.model.named_parameters()]
+    want = torch.cat([sdg[n].grad.reshape(-1) for n in names])
+    r = rel_l2(flat.cpu(), want)
+    print(f"{kind}: full-size single-image gradient rel-L2 vs oracle autograd = {r:.3e}")
+    assert r < GRAD_REL

@@ -202,6 +202,11 @@ def require_cuda_tensor(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError(f"{name}: expected a contiguous tensor")
+    # The library launches on the CURRENT device and on its current stream (stream_ptr): a tensor of another GPU
+    # would be an illegal address -- or, with peer access on, a silent run on the wrong GPU.
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{name}: tensor lives on {t.device} but the current device is cuda:"
+                           f"{torch.cuda.current_device()}; call torch.cuda.set_device / use torch.cuda.device(...)")
 
 
 STRETCH_MODES = {"linear": 0, "sqrt": 1, "asinh": 2, "log": 3}

@@ -59,7 +59,10 @@ class Model(_Base):
                 self.log(k, v)
 
     def forward(self, x) -> Tensor:
-        return torch.clamp(self.model(x), min=0.0, max=1.0)
+        y = self.model(x)
+        if getattr(self.model, "output_is_clamped", False):
+            return y  # already in [0, 1]: the second clamp is the identity (value and gradient)
+        return torch.clamp(y, min=0.0, max=1.0)
 
     def training_step(self, batch, batch_idx=0):
         return self._on_step(batch, "train")

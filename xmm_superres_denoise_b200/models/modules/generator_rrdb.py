@@ -9,6 +9,7 @@ whose backward is the hand-written data/weight-gradient kernels.
 """
 from __future__ import annotations
 
+import contextlib
 import functools
 import math
 
@@ -20,6 +21,10 @@ from . import RRDB, make_layer
 
 class _GeneratorRRDB(nn.Module):
     _kind = "trunk"
+    # GeneratorRRDB_SR / _DN outputs leave the conv_last kernel already clamped to [0, 1] (generator_rrdb.py:109,136),
+    # so Model.forward's second clamp (models/model.py:48-49) is the identity -- value and gradient -- and callers
+    # that see this flag skip the extra elementwise pass (354 MB of traffic per batch-64 SR step).
+    output_is_clamped = True
 
     def __init__(self, in_channels: int, out_channels: int, num_filters: int, num_res_blocks: int,
                  memory_efficient: bool = False):
@@ -64,11 +69,14 @@ class _GeneratorRRDB(nn.Module):
 
     def forward(self, x):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad:
-            from ...autograd_fn import generator_apply
+        # libxmm_b200 launches on the CURRENT device / stream: make the input's GPU current for the call, so
+        # `model.to("cuda:1")(x)` works without torch.cuda.set_device(1) (CPU tensors are rejected by the engine)
+        with torch.cuda.device(x.device) if x.is_cuda else contextlib.nullcontext():
+            if needs_grad:
+                from ...autograd_fn import generator_apply
 
-            return generator_apply(self, x)
-        return self._get_engine().forward_inference(x)
+                return generator_apply(self, x)
+            return self._get_engine().forward_inference(x)
 
 
 class GeneratorRRDB_SR(_GeneratorRRDB):

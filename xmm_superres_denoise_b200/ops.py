@@ -6,6 +6,7 @@ bf16 ``[B, H, W, C]`` and a convolution reads / writes a *channel window* of the
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -84,14 +85,29 @@ def conv3x3(inp: torch.Tensor, in_coff: int, cin: int, wblob_ptr: int, kc: int, 
     colsum/colsum_scale (fused bias gradient: colsum += scale * column sums of the written values),
     wblob_row (the layer's row-hop weight image: lets the library pick conv3x3_row.cuh where the shape qualifies).
     See ``xmm_conv3x3_params`` in include/xmm_b200.h for the epilogue definition."""
+    if _TORCH_OPS and not (kw.keys() - _TORCH_FWD_KEYS):
+        # the registered dispatcher op (csrc/torch_ops.cpp) instead of ctypes: same launcher, same arguments
+        from . import torch_ops
+
+        torch_ops.load().conv3x3_fwd(inp, in_coff, cin, wblob_ptr, kc, cout, out, out_coff, kw.get("lrelu", 1.0),
+                                     kw.get("s0", 1.0), kw.get("r1"), kw.get("r1_coff", 0), kw.get("s1", 0.0),
+                                     kw.get("r2"), kw.get("r2_coff", 0), kw.get("s2", 0.0), kw.get("wblob_row") or 0,
+                                     kw.get("tap_mode", 0))
+        _count()
+        return
     p = Conv3x3Params()
     _conv3x3_params(p, inp, in_coff, cin, wblob_ptr, kc, cout, out, out_coff, **kw)
     _lib.check(_lib.load().xmm_conv3x3_bf16(ctypes.byref(p), _lib.stream_ptr()))
     _count()
 
 
+_TORCH_OPS = os.environ.get("XMM_TORCH_OPS", "0") == "1"
+_TORCH_FWD_KEYS = {"lrelu", "s0", "r1", "r1_coff", "s1", "r2", "r2_coff", "s2", "wblob_row", "tap_mode"}
+
+
 CHAIN_AUTO, CHAIN_PIPELINED, CHAIN_LAYER_BY_LAYER = 0, 1, 2
 _chain_ws: dict = {}
+_chain_ws_retired: list = []  # outgrown workspaces stay allocated: a captured CUDA graph may still hold their address
 
 
 def conv3x3_chain(layers, mode: int = CHAIN_AUTO) -> None:
@@ -108,6 +124,8 @@ def conv3x3_chain(layers, mode: int = CHAIN_AUTO) -> None:
     need = int(lib.xmm_conv3x3_chain_workspace_bytes(n, arr[0].batch, arr[0].height))
     ws = _chain_ws.get(dev)
     if ws is None or ws.numel() < need:
+        if ws is not None:
+            _chain_ws_retired.append(ws)
         ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
         _chain_ws[dev] = ws
     _lib.check(lib.xmm_conv3x3_chain_bf16(arr, n, int(mode), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))

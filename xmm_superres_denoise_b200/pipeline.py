@@ -56,7 +56,9 @@ class InferencePipeline:
                                          which="lr", exposure=self.exposure)
         self.ev_free[s].record(cur)
         with torch.no_grad():
-            y = torch.clamp(self.model(x), 0.0, 1.0)  # models/model.py:48-49
+            y = self.model(x)  # models/model.py:48-49
+            if not getattr(self.model, "output_is_clamped", False):  # our generators clamp in the conv_last epilogue
+                y = torch.clamp(y, 0.0, 1.0)
         if self.denormalize:
             y = self.norm.denormalize_hr_image(y)
         ready = torch.cuda.Event()

@@ -97,6 +97,9 @@ class FusedAdam:
         self.step_count = int(sd["step"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr = float(sd.get("lr", self.lr))
+        self.betas = tuple(float(b) for b in sd.get("betas", self.betas))
+        self.eps = float(sd.get("eps", self.eps))
 
 
 class TrainStep:
@@ -114,7 +117,13 @@ class TrainStep:
         self.model, self.loss, self.group = model, loss, group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.flat = flatten_parameters(model)
+        if self.world > 1:
+            # Lightning's DDP wrapper broadcasts rank 0's parameters when it wraps the module (train.py:148-155 of the
+            # reference): replicas must START identical -- they may have been seeded per rank or loaded from a
+            # checkpoint on one rank only -- because only gradients are exchanged afterwards.
+            dist.broadcast(self.flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self.engine = model._get_engine(train=True)
+        self.engine.arena.invalidate()  # packed bf16 weight images follow the (possibly replaced) parameters
         self.opt = FusedAdam(self.flat, lr, betas, on_update=self.engine.arena.invalidate)
         self.overlap = overlap_allreduce and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.overlap else None

@@ -91,7 +91,9 @@ def infer_files(fits_files: Sequence, dataset_config: dict, out_path, generator:
         x = load_and_combine_simulations(lr_res, counts_d, det_mask=mask_dev, normalizer=norm, which="lr",
                                          exposure=expo.to(dev))
         with torch.no_grad():
-            pred = torch.clamp(generator(x), 0.0, 1.0)  # models/model.py:48-49
+            pred = generator(x)  # models/model.py:48-49
+            if not getattr(generator, "output_is_clamped", False):
+                pred = torch.clamp(pred, 0.0, 1.0)
         in_denorm = norm.denormalize_lr_image(x).cpu().numpy()
         out_denorm = norm.denormalize_hr_image(pred).cpu().numpy()
         res_mult = out_denorm.shape[-1] // in_denorm.shape[-1]
