@@ -319,6 +319,11 @@ def bench_train(args, kind: str, dev, dist, rank: int, world: int, local_rank: i
 
 def main() -> None:
     global NF, NB
+    # watchdog: a deadlocked kernel would otherwise sit in cudaDeviceSynchronize until the caller's limit; after
+    # XMM_BENCH_WATCHDOG seconds (default 900) without finishing, dump every thread's Python stack to stderr and exit
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("XMM_BENCH_WATCHDOG", "900")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -121,14 +121,23 @@ int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);
 
 /* A chain of dependent 3x3 convolutions -- the five convs of one ResidualDenseBlock_5C.forward
  * (rrdb_blocks.py:37-54: each reads what the previous ones wrote) or the five data gradients of its backward --
- * with the SAME result as calling xmm_conv3x3_bf16 on layers[0], layers[1], ... in order.
- * mode 0: library chooses; 1: one pipelined launch (layer k runs on its own group of SMs two image strips behind
- * layer k-1, so intermediate activations are consumed from L2; error if the layers do not qualify); 2: layer by
- * layer.  Pipelining needs kc = cout = 32, one image geometry, no pixel shuffle, and no write-after-read between
- * layers; masks / residuals must not be produced inside the chain.  `workspace` (device, borrowed for the call,
- * xmm_conv3x3_chain_workspace_bytes) holds the strip-completion counters.                                      */
+ * with the SAME result (up to fp32 summation order) as calling xmm_conv3x3_bf16 on layers[0], layers[1], ... in order.
+ * mode_flags = mode | flags.
+ * mode 0: library chooses (the fused dense block where the layers qualify, else layer by layer);
+ *      1: one pipelined launch (layer k runs on its own group of SMs two image strips behind layer k-1, so
+ *         intermediate activations are consumed from L2; error if the layers do not qualify; needs `workspace`,
+ *         xmm_conv3x3_chain_workspace_bytes);
+ *      2: layer by layer;
+ *      3: fused dense block (conv3x3_rdb.cuh): conv1..conv3 in one launch and conv4..conv5 in a second, the feature
+ *         maps in between handed over in shared memory (576 instead of 1280 bytes per pixel through HBM); error if
+ *         the layers are not exactly a dense block: five kc = cout = 32 layers with a row-hop weight image
+ *         (wblob_row), layer k reading channels [c0, c0 + 32 (k+1)) of ONE buffer and, for k < 5, writing channels
+ *         [c0 + 32 k, c0 + 32 (k+1)) of it; LeakyReLU / residuals (last layer only) as usual; even image height.
+ * XMM_CHAIN_SKIP_DEAD_STORES: the caller will not read the outputs of layers 1..n-1 after this call (inference);
+ *         outputs that no later launch of the chain reads need not be written (the fused form never writes x4).   */
+#define XMM_CHAIN_SKIP_DEAD_STORES 0x100
 size_t xmm_conv3x3_chain_workspace_bytes(int nlayers, int batch, int height);
-int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode, void* workspace,
+int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode_flags, void* workspace,
                            size_t workspace_bytes, void* stream);
 
 /* Input transforms ------------------------------------------------------------------- */

@@ -458,6 +458,107 @@ def test_conv3x3_chain_pipelined_is_bit_identical_to_layer_by_layer(dev, b, h, w
     assert rel_l2(p[1][..., :f].float().permute(0, 3, 1, 2), y5) < 6e-3
 
 
+# ------------------------------------------------------------------------------ fused dense block (conv3x3_rdb.cuh)
+def _dense_block_case(dev, b, h, w, seed, third_rdb):
+    from xmm_superres_denoise_b200.engine import WeightArena, _Blob, _Segment
+
+    f = 32
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(b, h, w, f, generator=g).to(torch.bfloat16)
+    xr = torch.randn(b, h, w, f, generator=g).to(torch.bfloat16)
+    ws = [(torch.randn(f, k * f, 3, 3, generator=g) * 0.05).to(dev) for k in range(1, 6)]
+    bs = [(torch.randn(f, generator=g) * 0.1).to(dev) for _ in range(5)]
+    arena = WeightArena()
+    for k in range(1, 6):
+        arena.add(_Blob(f"c{k}", f, 32, k, [_Segment(ws[k - 1], k * f, 0, 0, 0, 0, k * f, 1.0)], bs[k - 1]))
+        arena.add(_Blob(f"c{k}.row", f, 32, k, [_Segment(ws[k - 1], k * f, 0, 0, 0, 0, k * f, 1.0)], bs[k - 1], tap_order=1))
+    arena.ensure(dev)
+
+    def layers(buf, nxt, res):
+        ls = [((buf, 0, k * f, arena.ptr(f"c{k}"), 32, f, buf, k * f), dict(lrelu=0.2, wblob_row=arena.ptr(f"c{k}.row")))
+              for k in range(1, 5)]
+        kw = dict(s0=0.04, r1=buf, r1_coff=0, s1=0.2, r2=res, r2_coff=0, s2=1.0) if third_rdb else \
+            dict(s0=0.2, r1=buf, r1_coff=0, s1=1.0)
+        ls.append(((buf, 0, 5 * f, arena.ptr("c5"), 32, f, nxt, 0), dict(wblob_row=arena.ptr("c5.row"), **kw)))
+        return ls
+
+    # the block in torch: bf16 feature maps between the layers, as the kernels keep them (rrdb_blocks.py:37-54,66-70)
+    cur = x0.float().permute(0, 3, 1, 2)
+    feats = [cur]
+    for k in range(1, 5):
+        y = F.leaky_relu(F.conv2d(torch.cat(feats, 1), ws[k - 1].cpu().to(torch.bfloat16).float(), bs[k - 1].cpu(),
+                                  padding=1), 0.2)
+        feats.append(y.to(torch.bfloat16).float())
+    y5 = F.conv2d(torch.cat(feats, 1), ws[4].cpu().to(torch.bfloat16).float(), bs[4].cpu(), padding=1)
+    want = (0.04 * y5 + 0.2 * cur + xr.float().permute(0, 3, 1, 2)) if third_rdb else (0.2 * y5 + cur)
+    return x0, xr, layers, feats, want, arena
+
+
+@pytest.mark.parametrize("b,h,w,third", [(1, 8, 16, False), (2, 48, 40, True), (3, 100, 64, False), (2, 26, 130, True),
+                                         (1, 416, 416, True), (5, 64, 48, False)])
+def test_conv3x3_fused_dense_block_matches_torch_and_layer_by_layer(dev, b, h, w, third):
+    """xmm_conv3x3_chain_bf16 mode 3 (conv1-3 in one launch, conv4-5 in a second, feature maps handed over in shared
+    memory) on one ResidualDenseBlock_5C.forward (rrdb_blocks.py:37-54; `third`: the RRDB-closing block with both
+    residuals, rrdb_blocks.py:70): x1..x4 and the block output against torch conv2d and against the layer-by-layer
+    launches; untouched channels stay untouched; with SKIP_DEAD_STORES x4 is not written and the output is the same."""
+    from xmm_superres_denoise_b200 import ops
+
+    f = 32
+    x0, xr, layers, feats, want, _arena = _dense_block_case(dev, b, h, w, 77 * b + h + w, third)
+    res = {}
+    for mode in (ops.CHAIN_LAYER_BY_LAYER, ops.CHAIN_FUSED, ops.CHAIN_FUSED | ops.CHAIN_SKIP_DEAD_STORES, ops.CHAIN_AUTO):
+        buf = torch.full((b, h, w, 5 * f + 32), -7.0, dtype=torch.bfloat16, device=dev)
+        buf[..., :f] = x0.to(dev)
+        nxt = torch.full((b, h, w, 2 * f), 5.0, dtype=torch.bfloat16, device=dev)
+        ops.conv3x3_chain(layers(buf, nxt, xr.to(dev)), mode)
+        torch.cuda.synchronize()
+        res[mode] = (buf.cpu(), nxt.cpu())
+    fused = res[ops.CHAIN_FUSED]
+    assert torch.equal(fused[0][..., :f], x0) and torch.all(fused[0][..., 5 * f:] == -7.0) and torch.all(fused[1][..., f:] == 5.0)
+    for k in range(1, 5):
+        got = fused[0][..., k * f:(k + 1) * f].float().permute(0, 3, 1, 2)
+        assert rel_l2(got, feats[k]) < 4e-3, f"x{k}"
+    assert rel_l2(fused[1][..., :f].float().permute(0, 3, 1, 2), want) < 6e-3
+    lbl = res[ops.CHAIN_LAYER_BY_LAYER]
+    assert rel_l2(fused[0].float()[..., f:5 * f], lbl[0].float()[..., f:5 * f]) < 4e-3
+    assert rel_l2(fused[1].float()[..., :f], lbl[1].float()[..., :f]) < 6e-3
+    skip = res[ops.CHAIN_FUSED | ops.CHAIN_SKIP_DEAD_STORES]
+    assert torch.equal(skip[1], fused[1]) and torch.equal(skip[0][..., :4 * f], fused[0][..., :4 * f])
+    assert torch.all(skip[0][..., 4 * f:] == -7.0)  # x4 never left the SM
+    auto = res[ops.CHAIN_AUTO]
+    assert torch.equal(auto[0], fused[0]) and torch.equal(auto[1], fused[1])  # the default is the fused form
+
+
+def test_conv3x3_fused_dense_block_is_batch_invariant_and_rejects_other_chains(dev):
+    """The accumulator slot of a row is a function of the row index, not of the work split: an image computed alone
+    (148 CTAs share 7 columns) has the same bits as inside a batch; chains that are not a dense block are refused in
+    mode 3 and run layer by layer in mode 0."""
+    from xmm_superres_denoise_b200 import ops
+
+    f = 32
+    b, h, w = 6, 64, 200
+    x0, xr, layers, _feats, _want, _arena = _dense_block_case(dev, b, h, w, 5, True)
+
+    def run(sel, mode=ops.CHAIN_FUSED):
+        buf = torch.zeros(len(sel), h, w, 5 * f, dtype=torch.bfloat16, device=dev)
+        buf[..., :f] = x0[sel].to(dev)
+        nxt = torch.zeros(len(sel), h, w, f, dtype=torch.bfloat16, device=dev)
+        ops.conv3x3_chain(layers(buf, nxt, xr[sel].to(dev)), mode)
+        torch.cuda.synchronize()
+        return buf, nxt
+
+    full = run(list(range(b)))
+    for i in (0, 4):
+        alone = run([i])
+        assert torch.equal(alone[0][0], full[0][i]) and torch.equal(alone[1][0], full[1][i])
+    buf = torch.zeros(1, 37, w, 5 * f, dtype=torch.bfloat16, device=dev)  # odd height: no two bands
+    nxt = torch.zeros(1, 37, w, f, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(RuntimeError, match="fuse"):
+        ops.conv3x3_chain(layers(buf, nxt, torch.zeros_like(nxt)), ops.CHAIN_FUSED)
+    ops.conv3x3_chain(layers(buf, nxt, torch.zeros_like(nxt)), ops.CHAIN_AUTO)  # falls back, no error
+    torch.cuda.synchronize()
+
+
 def test_conv3x3_chain_rejects_hazards(dev):
     from xmm_superres_denoise_b200 import ops
 
@@ -496,8 +597,9 @@ def test_generator_with_pipelined_chains_matches_default_path(dev, kind):
     e_pipe, e_def = rel_l2(outs[ops.CHAIN_PIPELINED], want), rel_l2(outs[ops.CHAIN_LAYER_BY_LAYER], want)
     print(f"{kind}: rel-L2 vs oracle pipelined {e_pipe:.3e}, layer by layer {e_def:.3e}")
     assert e_pipe < 1.5 * e_def + 1e-3
-    # two bf16 paths whose cin=32 layers accumulate in a different order (tap views vs column scatter)
-    assert rel_l2(outs[ops.CHAIN_PIPELINED], outs[ops.CHAIN_LAYER_BY_LAYER]) < REL_L2_BF16
+    # two bf16 paths that accumulate in a different order (column scatter vs row-hop): on this mostly-clamped output
+    # they sit as far from each other as each sits from the fp32 oracle
+    assert rel_l2(outs[ops.CHAIN_PIPELINED], outs[ops.CHAIN_LAYER_BY_LAYER]) < max(REL_L2_BF16, e_pipe, e_def)
     assert rel_l2(grads[ops.CHAIN_PIPELINED], grads[ops.CHAIN_LAYER_BY_LAYER]) < 1e-2
 
 

@@ -1,0 +1,567 @@
+// Fused dense-block convolutions: conv1..conv3 (or conv4..conv5) of one ResidualDenseBlock_5C.forward
+// (rrdb_blocks.py:37-54) in ONE kernel, the intermediate feature maps handed from layer to layer through shared memory.
+//
+// Why.  Layer by layer a dense block moves 1280 B per pixel through HBM (conv_k re-reads x0..x_{k-1}) for 135*F^2 MAC:
+// at batch 64 that is 2.2 ms of pure HBM time per block against 1.8 ms of tensor time, and every per-layer kernel of
+// round 1 / the row-hop kernel sits on that wall (3.75-4.6 TB/s whatever Cin, tools/row_probe.py).  Fusing 1-2-3 and
+// 4-5 leaves 64 + 192 B (read x0, write x1..x3) and 256 + 64 B (read x0..x3, write the block output): 576 B per pixel,
+// and the kernel becomes tensor-bound.
+//
+// Form.  The row-hop form of conv3x3_row.cuh (the three dy taps are the N = 96 columns of one MMA and land in the
+// accumulators of output rows r-1, r, r+1), on a tile that makes halo recompute cheap: M = 128 lanes = one image row of
+// TWO horizontal bands x 63 pixels.  In shared memory a row tile is 130 consecutive 64-byte pixel positions
+//     [halo | 63 px of band 0 | halo][halo | 63 px of band 1 | halo]
+// written by one 5-D TMA box (c, 65 px, 1 row, 2 bands); the dx taps are descriptor views one position apart, lane i
+// is centred on position i + 1 (lanes 63 / 64 are centred on the two inner halo positions and compute nothing useful).
+// A CTA walks a 63-pixel column of both bands top to bottom.  Layer l+1 consumes the rows layer l produced two steps
+// earlier: the epilogue writes them as bf16 into a ring of row tiles with the same swizzled layout a TMA load would
+// have produced, so they are MMA A operands as they are -- they never leave the SM unless a later kernel needs them
+// (then the epilogue also stores the lanes this tile owns).
+//
+// Halo recompute instead of halo exchange: with NL fused layers the lanes within NL-1-l pixels of a tile edge that
+// is not an image edge are wrong after layer l (their neighbours belong to another tile), so tile t+1 starts
+// 2*(NL-1) pixels before tile t ends and each tile stores only the pixels it owns (416 px = 7 tiles: 61 + 5*59 + 61
+// for three layers, 93 % of the lanes useful).  The same in y: a piece of rows [ra, rb) computes layer l on
+// [ra-e, rb+e), e = NL-1-l, from input rows of the neighbouring piece / band (recomputed, not stored).  Rows and
+// pixels outside the image are ZERO in every intermediate map (Conv2d's padding is per layer), so the epilogue
+// writes zeros there.
+//
+// Accumulators.  Layer l owns 5 TMEM slots of 32 columns.  The step on input row r targets the window
+// (c, c+1, c+2), c = (r-1) mod 3, i.e. slots are a function of the ROW INDEX, not of a running counter: the result
+// does not depend on how the work is split (batch invariance is bit-exact).  A row whose window position is 0 or 1
+// collected its first partial sums in slots 3 / 4 (the window slid over the ring end); the epilogue adds the two
+// slots.  Every MMA accumulates: the epilogue zeroes a slot after draining it, and the issuer starts the step on
+// row r only after row r-2 has been drained (one barrier pair per layer, strictly alternating).
+//
+// Schedule.  One deterministic walk (rdb_walk) interleaves the layers -- L0 step, L1 step, L2 step, L0 step ... --
+// and is run identically by the TMA producer, the MMA issuer and the two epilogue groups.  Layer l may take its step
+// on row r when layer l-1 issued its step on row r+1 in an EARLIER round, so the rows it waits for were produced a
+// full round of MMAs ago and the tensor pipe does not drain while the epilogue works.  After the last row of a piece
+// a layer takes two flush steps (no MMAs) that complete and zero the two trailing partial rows.
+#pragma once
+#include <cstdio>
+
+#include "conv3x3_tc.cuh"
+
+namespace xmm {
+
+constexpr int kRdbP = 63;                         // pixels of one band segment (lanes per band, minus the junk lane)
+constexpr int kRdbBoxPx = kRdbP + 2;              // segment + both halo pixels
+constexpr int kRdbTileData = 2 * kRdbBoxPx * 64;  // bytes one TMA box writes (32 bf16 channels per pixel)
+constexpr int kRdbTileBytes = 17 * 512;           // tile pitch: whole SWIZZLE_64B atoms
+constexpr int kRdbThreads = 320;                  // producer warp, issuer warp, 2 x 4 epilogue warps
+constexpr int kRdbSlots = 5;                      // accumulator slots per layer
+constexpr int kRdbSlotCols = kRdbSlots * 32;
+constexpr int kRdbMaxRing = 8;
+constexpr int kRdbMaxStages = 8;
+constexpr int kRdbTapBytes = 32 * 64;             // one (dx, dy) block of a chunk: 32 output channels x 32 inputs
+
+struct RdbLayerArgs {
+  const void* wblob;   // row-hop order [chunk][dx][2 - dy][32][32] bf16 (SWIZZLE_64B applied) + 32 fp32 biases
+  uint32_t w_bytes;    // without the biases
+  uint32_t smem_off;   // where this layer's image starts in the weight region (1024-aligned)
+  float lrelu_slope;   // 1 = none
+  int store;           // the output is needed outside the kernel
+  __nv_bfloat16* out;
+  int out_ctot, out_coff;
+};
+
+struct RdbArgs {
+  RdbLayerArgs layer[3];
+  int cin_off;                 // channel of x0 in the input buffer (x_j at cin_off + 32 j)
+  int batch, height, width, band_h, tiles_x;
+  long long total_rows;        // batch * tiles_x * band_h (rows of all columns)
+  int stages, ring0, ring1;    // TMA stages; row tiles of the first / second in-CTA map
+  uint32_t w_total;            // bytes of the weight region
+  // residuals of the LAST layer (conv5: out = s0 * v + s1 * r1 + s2 * r2, rrdb_blocks.py:54,70)
+  float s0, s1, s2;
+  const __nv_bfloat16* r1;
+  int r1_ctot, r1_coff;
+  const __nv_bfloat16* r2;
+  int r2_ctot, r2_coff;
+  long long* prof;  // optional (XMM_RDB_PROF=1): 16 cycle counters per CTA, see launch_rdb
+};
+
+template <int NL>
+__host__ __device__ inline int rdb_tile_origin(int t) {  // first owned pixel of tile t
+  return t == 0 ? 0 : (kRdbP - (NL - 1)) + (t - 1) * (kRdbP - 2 * (NL - 1));
+}
+template <int NL>
+__host__ __device__ inline int rdb_tiles_x(int width) {
+  int n = 1;
+  while ((n == 1 ? 0 : rdb_tile_origin<NL>(n - 1) - (NL - 1)) + kRdbP < width) ++n;
+  return n;
+}
+
+struct RdbPiece {
+  int b, x0;            // image, pixel of lane 0 of each band
+  int own_lo, own_hi;   // pixels this tile stores
+  int ra, rb;           // rows (band-local) this piece stores
+};
+
+// The CTA's share of the work: the rows of all (image, tile) columns, in column order, cut into gridDim.x equal
+// contiguous ranges; a range touches a few columns = pieces.
+template <int NL>
+struct RdbSched {
+  int band_h, tiles_x, width, c0, npieces;
+  long long t0, t1;
+  __device__ __forceinline__ void init(const RdbArgs& a) {
+    band_h = a.band_h;
+    tiles_x = a.tiles_x;
+    width = a.width;
+    t0 = a.total_rows * blockIdx.x / gridDim.x;
+    t1 = a.total_rows * (blockIdx.x + 1) / gridDim.x;
+    c0 = int(t0 / band_h);
+    npieces = t1 > t0 ? int((t1 - 1) / band_h) - c0 + 1 : 0;
+  }
+  __device__ __forceinline__ RdbPiece get(int i) const {
+    RdbPiece p;
+    const int col = c0 + i;
+    const long long base = (long long)col * band_h;
+    p.ra = t0 > base ? int(t0 - base) : 0;
+    p.rb = t1 < base + band_h ? int(t1 - base) : band_h;
+    p.b = col / tiles_x;
+    const int t = col - p.b * tiles_x;
+    p.own_lo = rdb_tile_origin<NL>(t);
+    p.x0 = t == 0 ? 0 : p.own_lo - (NL - 1);
+    p.own_hi = t == tiles_x - 1 ? width : rdb_tile_origin<NL>(t + 1);
+    return p;
+  }
+};
+
+// The step sequence.  f(l, piece, r, flush, n, seq): layer l takes its step on input row r of `piece` (flush: one of
+// the two MMA-less steps after the piece's last row); n = how many steps layer l took before; seq[m] = sequence
+// number, among all rows of in-CTA map m, of the piece's first row ra - (NL-1-m).
+template <int NL, class F>
+__device__ __forceinline__ void rdb_walk(const RdbSched<NL>& s, F&& f) {
+  int piece[NL], r[NL], hi[NL], n[NL], seq[NL][NL];
+  RdbPiece pc[NL];
+  bool done[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    piece[l] = 0;
+    n[l] = 0;
+    done[l] = s.npieces == 0;
+#pragma unroll
+    for (int m = 0; m < NL; ++m) seq[l][m] = 0;
+    pc[l] = s.get(0);
+    r[l] = pc[l].ra - (NL - 1 - l) - 1;
+    hi[l] = pc[l].rb + (NL - 1 - l) + 2;
+  }
+  while (!done[NL - 1]) {
+    // Which layers step in this round, decided on the state at the START of the round: layer l steps when layer l-1
+    // took its step on row r+1 in an earlier round.  Steady state (the bulk of the walk): every layer is inside the
+    // same piece, two rows behind the layer before it, so all of them step once per round until the first one runs
+    // out of real rows -- `reps` rounds without a decision.
+    uint32_t go = done[0] ? 0u : 1u;
+    bool steady = !done[0];
+    int reps = pc[0].rb + (NL - 1) - r[0] + 1;  // real steps layer 0 has left in this piece
+#pragma unroll
+    for (int l = 1; l < NL; ++l) {
+      const bool ready = !done[l] && (done[l - 1] || piece[l - 1] > piece[l] || (piece[l - 1] == piece[l] && r[l - 1] > r[l] + 1));
+      go |= ready ? (1u << l) : 0u;
+      steady = steady && ready && piece[l] == piece[0];
+      const int kl = pc[l].rb + (NL - 1 - l) - r[l] + 1;
+      reps = kl < reps ? kl : reps;
+    }
+    if (!steady || reps < 1) reps = 1;
+    for (int i = 0; i < reps; ++i) {
+#pragma unroll
+      for (int l = 0; l < NL; ++l) {
+        if ((go >> l) & 1u) {
+          const int e = NL - 1 - l;
+          f(l, pc[l], r[l], r[l] > pc[l].rb + e, n[l], seq[l]);
+          ++n[l];
+          if (++r[l] > hi[l]) {
+#pragma unroll
+            for (int m = 0; m < NL; ++m) seq[l][m] += (pc[l].rb - pc[l].ra) + 2 * (NL - 1 - m);
+            if (++piece[l] >= s.npieces) {
+              done[l] = true;
+            } else {
+              pc[l] = s.get(piece[l]);
+              r[l] = pc[l].ra - e - 1;
+              hi[l] = pc[l].rb + e + 2;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// mbarrier wait with a watchdog: a wait that spins for ~seconds reports who waits for what and traps (a wedged
+// schedule must fail loudly instead of hanging the process).
+__device__ __noinline__ void rdb_wait_timeout(int tag, int a, int b2, int c) {
+  printf("conv3x3_rdb: CTA %d thread %d stuck in wait %d (layer/map %d, index %d, parity %d)\n", int(blockIdx.x),
+         int(threadIdx.x), tag, a, b2, c);
+  __trap();
+}
+__device__ __forceinline__ void rdb_wait(uint64_t* bar, uint32_t parity, int tag, int a, int b2) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) rdb_wait_timeout(tag, a, b2, int(parity));
+  }
+}
+
+// the same, adding the cycles spent waiting to `acc` when profiling
+#ifndef XMM_RDB_PROFILE
+#define XMM_RDB_PROFILE 0  // 1: cycle counters of the issuer (XMM_RDB_PROF=1 prints them per launch)
+#endif
+__device__ __forceinline__ void rdb_wait_p(uint64_t* bar, uint32_t parity, int tag, int a, int b2, bool prof, long long& acc) {
+  if (XMM_RDB_PROFILE && prof) {
+    const long long t0 = clock64();
+    rdb_wait(bar, parity, tag, a, b2);
+    acc += clock64() - t0;
+  } else {
+    rdb_wait(bar, parity, tag, a, b2);
+  }
+}
+
+__device__ __forceinline__ int rdb_phi(int row) { return (row + 30) % 3; }  // window position of a row (row >= -30)
+
+__device__ __forceinline__ void tmem_st_zero32(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// G: feature maps read from global memory (x0 .. x_{G-1}); NL: fused layers.  Layer l (0-based) is conv_{G+l}: its K
+// chunks are the G global maps then the l maps produced in this CTA.
+template <int G, int NL>
+__global__ void __launch_bounds__(kRdbThreads, 1)
+conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs args) {
+  static_assert(NL == 2 || NL == 3, "two or three fused layers");
+  static_assert(NL * kRdbSlotCols <= 512, "accumulators exceed TMEM");
+  constexpr int NM = NL - 1;  // in-CTA maps
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* stage_s = smem + args.w_total;
+  uint8_t* map_s[2];
+  map_s[0] = stage_s + size_t(args.stages) * kRdbTileBytes;
+  map_s[1] = map_s[0] + size_t(args.ring0) * kRdbTileBytes;
+  constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};  // row tiles of the in-CTA maps (== args.ring0 / ring1, checked by the host)
+  uint8_t* after = map_s[1] + size_t(NM > 1 ? args.ring1 : 0) * kRdbTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = full_bar + kRdbMaxStages;
+  uint64_t* tfull_bar = empty_bar + kRdbMaxStages;  // [NL][2]: one per (layer, epilogue group that drains the row)
+  uint64_t* tdrain_bar = tfull_bar + 6;             // [NL][2]
+  uint64_t* mfull_bar = tdrain_bar + 6;             // [2][kRdbMaxRing]
+  uint64_t* mempty_bar = mfull_bar + 2 * kRdbMaxRing;
+  uint64_t* w_bar = mempty_bar + 2 * kRdbMaxRing;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_in);
+    for (int s = 0; s < args.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int l = 0; l < 2 * NL; ++l) {
+      ptx::mbar_init(&tfull_bar[l], 1);
+      ptx::mbar_init(&tdrain_bar[l], 4);  // the four warps of the group that drained the row
+    }
+    for (int m = 0; m < NM; ++m)
+      for (int s = 0; s < ring[m]; ++s) {
+        ptx::mbar_init(&mfull_bar[m * kRdbMaxRing + s], 4);
+        ptx::mbar_init(&mempty_bar[m * kRdbMaxRing + s], 1);  // the commit of the row's last reader
+      }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp >= 2) {
+    // accumulators start at zero (every MMA accumulates); halo positions of the map tiles stay zero for ever
+    if (warp < 6) {
+      const uint32_t lane_base = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+      for (int s = 0; s < NL * kRdbSlots; ++s) tmem_st_zero32(lane_base + uint32_t(s * 32));
+      tmem_st_wait();
+    }
+    uint4* z = reinterpret_cast<uint4*>(map_s[0]);
+    const int nz = (args.ring0 + (NM > 1 ? args.ring1 : 0)) * (kRdbTileBytes / 16);
+    for (int i = int(threadIdx.x) - 64; i < nz; i += kRdbThreads - 64) z[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  RdbSched<NL> sched;
+  sched.init(args);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      uint32_t wtot = 0;
+      for (int l = 0; l < NL; ++l) wtot += args.layer[l].w_bytes + 128u;
+      ptx::mbar_expect_tx(w_bar, wtot);
+      for (int l = 0; l < NL; ++l) {
+        const uint8_t* gsrc = static_cast<const uint8_t*>(args.layer[l].wblob);
+        const uint32_t n_l = args.layer[l].w_bytes + 128u;
+        for (uint32_t off = 0; off < n_l; off += 32768u)
+          ptx::bulk_load(w_s + args.layer[l].smem_off + off, gsrc + off, n_l - off < 32768u ? n_l - off : 32768u, w_bar);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int, const int*) {
+        if (flush) return;
+        // input row r of both bands; above / below a band: the neighbouring band's rows (outside the image: zeros)
+        int row = r, band0 = 0;
+        if (r < 0) {
+          row = r + args.band_h;
+          band0 = -1;
+        } else if (r >= args.band_h) {
+          row = r - args.band_h;
+          band0 = 1;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          rdb_wait(&empty_bar[stage], phase ^ 1u, 1, l, stage);
+          ptx::mbar_expect_tx(&full_bar[stage], kRdbTileData);
+          ptx::tma_load_5d(stage_s + size_t(stage) * kRdbTileBytes, &tmap_in, &full_bar[stage], args.cin_off + 32 * g,
+                           pc.x0 - 1, row, band0, pc.b);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      });
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      rdb_wait(w_bar, 0, 7, 0, 0);
+      ptx::tc_fence_after();
+      const uint64_t bdesc0 = ptx::umma_smem_desc(ptx::smem_u32(w_s), 16, 512, ptx::UMMA_SW64);
+      const uint64_t adesc0 = ptx::umma_smem_desc(ptx::smem_u32(stage_s), 16, 512, ptx::UMMA_SW64);
+      const uint32_t a_hi = uint32_t(adesc0 >> 32), b_hi = uint32_t(bdesc0 >> 32);
+      const uint32_t a_lo0 = uint32_t(adesc0), b_lo0 = uint32_t(bdesc0);
+      const uint32_t a_map0[2] = {a_lo0 + uint32_t((map_s[0] - stage_s) >> 4), a_lo0 + uint32_t((map_s[1] - stage_s) >> 4)};
+      constexpr uint32_t kTile16 = uint32_t(kRdbTileBytes) >> 4;
+      constexpr uint32_t kTap16 = uint32_t(kRdbTapBytes) >> 4;
+      constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, 96, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto issue6 = [&](uint32_t d, uint32_t a, uint32_t b) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            ptx::umma_ss_lh<true>(d, a + uint32_t((dx * 64 + ks * 32) >> 4), a_hi,
+                                  b + uint32_t(dx * 3) * kTap16 + uint32_t((ks * 32) >> 4), b_hi, kIdesc);
+      };
+      // Completed rows go to the two epilogue groups alternately (in walk order).  Every barrier has ONE waiter that
+      // sees each of its phases: (layer, group) pairs have their own "row complete" / "row drained" barriers, and
+      // the k-th use of a pair is phase k.
+      const bool prof = XMM_RDB_PROFILE && args.prof != nullptr;
+      long long pw[3] = {0, 0, 0};
+      const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
+      uint32_t task = 0;
+      uint32_t use_par = 0;  // bit 2l+g: parity of how often (layer l, group g) has been used
+      uint32_t prev_bar[NL], prev_par[NL];
+#pragma unroll
+      for (int l = 0; l < NL; ++l) prev_bar[l] = prev_par[l] = 0;
+      rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int n, const int* seq) {
+        const uint32_t pair = uint32_t(2 * l) + ((task++) & 1u);
+        // the row completed by the layer's previous step is out of its accumulator slots
+        if (n > 0) rdb_wait_p(&tdrain_bar[prev_bar[l]], prev_par[l], 2, l, n, prof, pw[0]);
+        ptx::tc_fence_after();
+        if (!flush) {
+          const uint32_t d = tmem_base + uint32_t(l * kRdbSlotCols + rdb_phi(r - 1) * 32);
+          const uint32_t b_l = b_lo0 + (args.layer[l].smem_off >> 4);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            rdb_wait_p(&full_bar[stage], phase, 3, l, stage, prof, pw[1]);
+            ptx::tc_fence_after();
+            issue6(d, a_lo0 + uint32_t(stage) * kTile16, b_l + uint32_t(g * 9) * kTap16);
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == args.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < NM; ++m)
+            if (m < l) {
+              const int sq = seq[m] + (r - (pc.ra - (NL - 1 - m)));
+              const int slot = sq % ring[m];
+              rdb_wait_p(&mfull_bar[m * kRdbMaxRing + slot], uint32_t(sq / ring[m]) & 1u, 4, l * 10 + m, sq, prof, pw[2]);
+              ptx::tc_fence_after();
+              issue6(d, a_map0[m] + uint32_t(slot) * kTile16, b_l + uint32_t((G + m) * 9) * kTap16);
+              // the last layer that reads this row gives the tile back: layer l+1 reads rows [ra-e, rb+e-1], e = NL-1-l
+              const int e = NL - 1 - l;
+              if (l == NL - 1 || r < pc.ra - e || r > pc.rb + e - 1) ptx::umma_commit(&mempty_bar[m * kRdbMaxRing + slot]);
+            }
+        }
+        ptx::umma_commit(&tfull_bar[pair]);  // row r-1 of layer l is complete
+        prev_bar[l] = pair;
+        prev_par[l] = (use_par >> pair) & 1u;
+        use_par ^= 1u << pair;
+      });
+      if (XMM_RDB_PROFILE && prof) {
+        long long* o = args.prof + size_t(blockIdx.x) * 16;
+        o[0] = clock64() - t_begin;
+        o[1] = pw[0];
+        o[2] = pw[1];
+        o[3] = pw[2];
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    rdb_wait(w_bar, 0, 8, 0, 0);  // biases ride with the weights
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int group = (warp - 2) >> 2;  // takes every other completed row
+    const int pos = q * 32 + lane + 1;  // pixel position of this lane in a row tile
+    const int band = pos >= kRdbBoxPx ? 1 : 0;
+    const int pl = band ? pos - (kRdbBoxPx + 1) : pos - 1;  // pixel within the band segment
+    const bool lane_ok = band ? pl >= 0 : pl < kRdbP;
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t pos_off = uint32_t(pos) * 64u;
+    const uint32_t pos_xor = uint32_t(pos >> 1) & 3u;
+    const bool prof = XMM_RDB_PROFILE && args.prof != nullptr;
+    long long pw[2] = {0, 0};
+    long long ntask = 0;
+    const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
+    uint32_t task = 0;
+    uint32_t use_par = 0;  // bit l: parity of how many rows of layer l this group drained
+    rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int n, const int* seq) {
+      if (int((task++) & 1u) != group) return;
+      const uint32_t kth = (use_par >> l) & 1u;
+      use_par ^= 1u << l;
+      const int j = r - 1;  // the row this step completed
+      const int e = NL - 1 - l;
+      const bool real = j >= pc.ra - e && j < pc.rb + e;
+      const int px = pc.x0 + pl;
+      const int y = band * args.band_h + j;
+      const bool inimg = lane_ok && px < args.width && y >= 0 && y < args.height;
+      const bool owned = real && inimg && px >= pc.own_lo && px < pc.own_hi && j >= pc.ra && j < pc.rb;
+      const size_t pix = (size_t(pc.b) * args.height + size_t(y < 0 ? 0 : y)) * args.width + size_t(px < 0 ? 0 : px);
+      // residuals of the last layer: requested before the accumulator is waited for
+      uint4 res1[4], res2[4];
+      const bool last = l == NL - 1;
+      const bool has_r1 = last && args.r1 != nullptr, has_r2 = last && args.r2 != nullptr;
+      if (has_r1 && owned) {
+        const uint4* p = reinterpret_cast<const uint4*>(args.r1 + pix * args.r1_ctot + args.r1_coff);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) res1[k] = __ldg(p + k);
+      }
+      if (has_r2 && owned) {
+        const uint4* p = reinterpret_cast<const uint4*>(args.r2 + pix * args.r2_ctot + args.r2_coff);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) res2[k] = __ldg(p + k);
+      }
+      rdb_wait_p(&tfull_bar[2 * l + group], kth, 5, l, n, prof, pw[0]);
+      ++ntask;
+      ptx::tc_fence_after();
+      const int phi = rdb_phi(j);
+      const uint32_t t_main = lane_base + uint32_t(l * kRdbSlotCols + phi * 32);
+      const uint32_t t_carry = lane_base + uint32_t(l * kRdbSlotCols + (3 + phi) * 32);
+      uint32_t accr[32];
+      ptx::tmem_ld_32x32(t_main, accr);
+      float v[32];
+      if (phi < 2) {  // the row's first partial sums were collected in a carry slot
+        uint32_t car[32];
+        ptx::tmem_ld_32x32(t_carry, car);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(car[k]) + __uint_as_float(accr[k]);
+        tmem_st_zero32(t_carry);
+      } else {
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(accr[k]);
+      }
+      tmem_st_zero32(t_main);
+      tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tdrain_bar[2 * l + group]);
+      if (!real) return;
+
+      const float* bias_s = reinterpret_cast<const float*>(w_s + args.layer[l].smem_off + args.layer[l].w_bytes);
+      const float slope = args.layer[l].lrelu_slope;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * k);
+        v[4 * k] += b4.x;
+        v[4 * k + 1] += b4.y;
+        v[4 * k + 2] += b4.z;
+        v[4 * k + 3] += b4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
+      if (last) {
+        const float s0 = args.s0;
+        if (s0 != 1.f) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] *= s0;
+        }
+        if (has_r1 && owned) {
+          const float s1 = args.s1;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float m8[8];
+            unpack8(res1[k], m8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * k + i] = fmaf(s1, m8[i], v[8 * k + i]);
+          }
+        }
+        if (has_r2 && owned) {
+          const float s2 = args.s2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float m8[8];
+            unpack8(res2[k], m8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * k + i] = fmaf(s2, m8[i], v[8 * k + i]);
+          }
+        }
+      }
+      uint4 o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = pack8(v + 8 * k);
+      if (l < NL - 1) {
+        // the next layers' A operand: row j of map l, swizzled as a TMA load would have written it; zeros outside
+        // the image (padding) and on the junk lanes
+        const int sq = seq[l] + (j - (pc.ra - e));
+        const int slot = sq % ring[l];
+        rdb_wait_p(&mempty_bar[l * kRdbMaxRing + slot], (uint32_t(sq / ring[l]) & 1u) ^ 1u, 6, l, sq, prof, pw[1]);
+        uint8_t* dst = map_s[l] + size_t(slot) * kRdbTileBytes + pos_off;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + ((uint32_t(k) ^ pos_xor) << 4)) = inimg ? o[k] : zero;
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&mfull_bar[l * kRdbMaxRing + slot]);
+      }
+      if (args.layer[l].store && owned) {
+        uint4* gp = reinterpret_cast<uint4*>(args.layer[l].out + pix * args.layer[l].out_ctot + args.layer[l].out_coff);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gp[k] = o[k];
+      }
+    });
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace xmm

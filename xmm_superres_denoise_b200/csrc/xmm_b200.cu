@@ -7,6 +7,7 @@
 #include "conv3x3_chain.cuh"
 #include "conv3x3_dx.cuh"
 #include "conv3x3_row.cuh"
+#include "conv3x3_rdb.cuh"
 #include "conv3x3_tc.cuh"
 #include "edge_kernels.cuh"
 #include "host_common.cuh"
@@ -717,10 +718,126 @@ extern "C" size_t xmm_conv3x3_chain_workspace_bytes(int nlayers, int batch, int 
   return size_t(nlayers) * size_t(batch) * size_t((height + kDxTileH - 1) / kDxTileH) * sizeof(int);
 }
 
-extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode, void* workspace,
+// ----------------------------------------------------------------------------- fused dense block (conv3x3_rdb.cuh)
+// Why (if at all) the five layers are not one ResidualDenseBlock_5C.forward the fused kernels can take; nullptr = ok.
+const char* rdb_blocker(const xmm_conv3x3_params* L, int n, const DeviceInfo& dev) {
+  if (n != 5) return "five layers";
+  const xmm_conv3x3_params& p0 = L[0];
+  if (p0.height < 8 || (p0.height & 1)) return "image height must be even (two bands) and >= 8";
+  for (int k = 0; k < 5; ++k) {
+    const xmm_conv3x3_params& p = L[k];
+    if (p.kc != 32 || p.cout != 32) return "kc = cout = 32 layers only";
+    if (p.pixel_shuffle != 0 || p.mask != nullptr || p.colsum != nullptr) return "no pixel shuffle / mask / column sums";
+    if (p.wblob_row == nullptr) return "no row-hop weight image (wblob_row)";
+    if (p.tap_mode > 0) return "a kernel form is forced (tap_mode)";
+    if (p.batch != p0.batch || p.height != p0.height || p.width != p0.width) return "one image geometry";
+    if (p.in != p0.in || p.in_ctot != p0.in_ctot || p.in_coff != p0.in_coff || p.cin != 32 * (k + 1))
+      return "layer k must read channels [c0, c0 + 32 (k+1)) of one buffer";
+    if (k < 4) {
+      if (p.out != p0.in || p.out_ctot != p0.in_ctot || p.out_coff != p0.in_coff + 32 * (k + 1))
+        return "layer k < 5 must write channels [c0 + 32 k, c0 + 32 (k+1)) of the same buffer";
+      if (p.r1 != nullptr || p.r2 != nullptr || p.s0 != 1.0f) return "residuals only on the last layer";
+    } else {
+      if (p.out == p0.in && p.out_coff < p0.in_coff + 160 && p.out_coff + 32 > p0.in_coff)
+        return "the last layer may not overwrite the block's own feature maps";
+    }
+  }
+  if (size_t(dev.max_smem_optin) < 232448) return "needs 227 KB of shared memory per CTA";
+  return nullptr;
+}
+
+template <int G, int NL>
+int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo& dev, cudaStream_t stream) {
+  RdbArgs a{};
+  uint32_t off = 0;
+  for (int l = 0; l < NL; ++l) {
+    const xmm_conv3x3_params& p = L[l];
+    a.layer[l].wblob = p.wblob_row;
+    a.layer[l].w_bytes = uint32_t(p.cin / 32) * 9u * uint32_t(kRdbTapBytes);
+    a.layer[l].smem_off = off;
+    off += (a.layer[l].w_bytes + 128u + 1023u) & ~1023u;
+    a.layer[l].lrelu_slope = p.lrelu_slope;
+    a.layer[l].store = store[l] ? 1 : 0;
+    a.layer[l].out = static_cast<__nv_bfloat16*>(p.out);
+    a.layer[l].out_ctot = p.out_ctot;
+    a.layer[l].out_coff = p.out_coff;
+  }
+  a.w_total = off;
+  const xmm_conv3x3_params& pl = L[NL - 1];
+  a.cin_off = L[0].in_coff;
+  a.batch = L[0].batch;
+  a.height = L[0].height;
+  a.width = L[0].width;
+  a.band_h = a.height / 2;
+  a.tiles_x = rdb_tiles_x<NL>(a.width);
+  a.total_rows = (long long)a.batch * a.tiles_x * a.band_h;
+  a.s0 = pl.s0; a.s1 = pl.s1; a.s2 = pl.s2;
+  a.r1 = static_cast<const __nv_bfloat16*>(pl.r1); a.r1_ctot = pl.r1_ctot; a.r1_coff = pl.r1_coff;
+  a.r2 = static_cast<const __nv_bfloat16*>(pl.r2); a.r2_ctot = pl.r2_ctot; a.r2_coff = pl.r2_coff;
+  constexpr int kBarBytes = 512;
+  const long long room = (long long)dev.max_smem_optin - 1024 - kBarBytes - (long long)a.w_total;
+  int tiles = int(room / kRdbTileBytes);
+  a.ring0 = NL == 3 ? 5 : 3;
+  a.ring1 = NL == 3 ? 3 : 0;
+  a.stages = tiles - a.ring0 - a.ring1;
+  if (a.stages > kRdbMaxStages) a.stages = kRdbMaxStages;
+  static const int stages_env = env_int("XMM_RDB_STAGES", 0);
+  if (stages_env > 0 && stages_env < a.stages) a.stages = stages_env;
+  if (a.stages < 3) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3 (fused dense block): %d pipeline stages fit", a.stages);
+  CUtensorMap tmap;
+  int rc = cached_band_tmap(&tmap, L[0].in, a.batch, a.height, a.width, L[0].in_ctot, a.band_h, 2, 32, kRdbBoxPx, 2);
+  if (rc != XMM_OK) return rc;
+  rc = ensure_max_smem(reinterpret_cast<const void*>(conv3x3_rdb_kernel<G, NL>), dev);
+  if (rc != XMM_OK) return rc;
+  const size_t smem = 1024 + size_t(a.w_total) + size_t(a.stages + a.ring0 + a.ring1) * kRdbTileBytes + kBarBytes;
+  static const int max_ctas = env_int("XMM_RDB_MAX_CTAS", 0);
+  int grid = a.total_rows < dev.sm_count ? int(a.total_rows) : dev.sm_count;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  // XMM_RDB_PROF=1 (developer): per-CTA cycle counters of the issuer and the two epilogue groups, printed per launch
+  static const int prof_env = XMM_RDB_PROFILE ? env_int("XMM_RDB_PROF", 0) : 0;
+  static long long* prof_dev = nullptr;
+  if (prof_env) {
+    if (prof_dev == nullptr) XMM_CUDA_OK(cudaMalloc(&prof_dev, 16 * sizeof(long long) * 1024));
+    XMM_CUDA_OK(cudaMemsetAsync(prof_dev, 0, 16 * sizeof(long long) * 1024, stream));
+    a.prof = prof_dev;
+  }
+  conv3x3_rdb_kernel<G, NL><<<grid, kRdbThreads, smem, stream>>>(tmap, a);
+  XMM_CUDA_OK(cudaGetLastError());
+  if (prof_env) {
+    XMM_CUDA_OK(cudaStreamSynchronize(stream));
+    std::vector<long long> h(size_t(grid) * 16);
+    XMM_CUDA_OK(cudaMemcpy(h.data(), prof_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    static const char* names[12] = {"issuer total", "issuer wait drained", "issuer wait TMA", "issuer wait map row",
+                                    "epi0 total", "epi0 wait row complete", "epi0 wait map slot", "epi0 rows",
+                                    "epi1 total", "epi1 wait row complete", "epi1 wait map slot", "epi1 rows"};
+    fprintf(stderr, "conv3x3_rdb<%d,%d> grid %d stages %d:", G, NL, grid, a.stages);
+    for (int k = 0; k < 12; ++k) {
+      double sum = 0;
+      for (int c = 0; c < grid; ++c) sum += double(h[size_t(c) * 16 + k]);
+      fprintf(stderr, " %s %.0f;", names[k], sum / grid);
+    }
+    fprintf(stderr, "\n");
+  }
+  return XMM_OK;
+}
+
+// conv1..conv3 in one launch, conv4..conv5 in a second one.  skip_dead: x4 is read by nobody after this block
+// (inference), so it is never written.
+int launch_rdb_block(const xmm_conv3x3_params* L, bool skip_dead, const DeviceInfo& dev, cudaStream_t stream) {
+  const bool store_a[3] = {true, true, true};
+  int rc = launch_rdb<1, 3>(L, store_a, dev, stream);
+  if (rc != XMM_OK) return rc;
+  const bool store_b[2] = {!skip_dead, true};
+  return launch_rdb<4, 2>(L + 3, store_b, dev, stream);
+}
+
+extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode_flags, void* workspace,
                                       size_t workspace_bytes, void* stream) {
   XMM_REQUIRE(layers != nullptr && nlayers >= 1, "conv3x3_chain: no layers");
-  XMM_REQUIRE(mode >= 0 && mode <= 2, "conv3x3_chain: mode must be 0 (auto), 1 (pipelined) or 2 (layer by layer)");
+  const int mode = mode_flags & 0xff;
+  const bool skip_dead = (mode_flags & XMM_CHAIN_SKIP_DEAD_STORES) != 0;
+  XMM_REQUIRE(mode >= 0 && mode <= 3 && (mode_flags & ~(0xff | XMM_CHAIN_SKIP_DEAD_STORES)) == 0,
+              "conv3x3_chain: mode must be 0 (auto), 1 (pipelined), 2 (layer by layer) or 3 (fused dense block)");
   DeviceInfo dev;
   int rc = require_sm100(&dev);
   if (rc != XMM_OK) return rc;
@@ -728,20 +845,23 @@ extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlay
     rc = check_conv_params(layers[l]);
     if (rc != XMM_OK) return rc;
   }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // fused dense block (conv3x3_rdb.cuh): the default wherever the five layers are one ResidualDenseBlock_5C.forward
+  static const int rdb_env = env_int("XMM_RDB", 1);
+  if (mode == 3 || (mode == 0 && rdb_env)) {
+    const char* why_not = rdb_blocker(layers, nlayers, dev);
+    if (why_not == nullptr) return launch_rdb_block(layers, skip_dead, dev, s);
+    if (mode == 3) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3_chain: cannot fuse the dense block (%s)", why_not);
+  }
   const char* why = chain_blocker(layers, nlayers);
-  bool pipelined = mode != 2 && why == nullptr;
+  bool pipelined = mode == 1 && why == nullptr;
   if (mode == 1 && why != nullptr) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3_chain: cannot pipeline (%s)", why);
   if (pipelined) {
     const size_t need = xmm_conv3x3_chain_workspace_bytes(nlayers, layers[0].batch, layers[0].height);
     XMM_REQUIRE(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0,
                 "conv3x3_chain: workspace of %zu bytes needed (got %zu)", need, workspace_bytes);
-    if (mode == 0) {  // the pipeline needs a few waves of strip segments to fill
-      const long long strips = (long long)layers[0].batch * ((layers[0].height + kDxTileH - 1) / kDxTileH);
-      if (strips * 2 < 4LL * dev.sm_count) pipelined = false;
-    }
+    return launch_chain(layers, nlayers, dev, static_cast<int*>(workspace), s);
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pipelined) return launch_chain(layers, nlayers, dev, static_cast<int*>(workspace), s);
   for (int l = 0; l < nlayers; ++l) {
     rc = xmm_conv3x3_bf16(&layers[l], stream);
     if (rc != XMM_OK) return rc;

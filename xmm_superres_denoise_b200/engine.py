@@ -265,9 +265,11 @@ class RRDBEngine(_LayerPlans):
         else:
             self._last_blob = None
         self._bufs: Dict[tuple, Dict[str, torch.Tensor]] = {}
-        # how a dense block's five dependent convs are launched (ops.CHAIN_*): layer by layer is the measured
-        # optimum today; XMM_CHAIN_MODE=1 selects the pipelined single-launch kernel (F=32 only)
-        self.chain_mode = int(os.environ.get("XMM_CHAIN_MODE", ops.CHAIN_LAYER_BY_LAYER))
+        # how a dense block's five dependent convs are launched (ops.CHAIN_*): by default the library decides --
+        # the fused dense-block kernels (conv1-3 + conv4-5, conv3x3_rdb.cuh) where the layers qualify (F = 32, even
+        # image height), else layer by layer; XMM_CHAIN_MODE=2 forces layer by layer, 1 the pipelined single launch
+        self.chain_mode = int(os.environ.get("XMM_CHAIN_MODE", ops.CHAIN_AUTO))
+        self._keep_all = True  # set per forward: training keeps every block's x1..x4 for the backward pass
         # CUDA-graph replay of small-batch inference (XMM_CUDA_GRAPH=0 disables)
         self.use_graph = os.environ.get("XMM_CUDA_GRAPH", "1") != "0"
         self.graph_max_batch = 8
@@ -310,7 +312,8 @@ class RRDBEngine(_LayerPlans):
             layers += self._conv(f"{name}.{k}", buf, 0, k * f, buf, k * f, lrelu=0.2)
         layers += self._conv(f"{name}.5", buf, 0, 5 * f, out, 0, s0=s0, r1=buf, r1_coff=0, s1=s1, r2=r2, r2_coff=0, s2=s2)
         if len(layers) == 5:
-            ops.conv3x3_chain(layers, self.chain_mode)
+            # inference keeps nothing of a block but its output: x4 need not be written (training reads x1..x4 back)
+            ops.conv3x3_chain(layers, self.chain_mode | (0 if self._keep_all else ops.CHAIN_SKIP_DEAD_STORES))
         else:  # split layers (F=64): plain launches
             self._run(layers)
 
@@ -321,6 +324,7 @@ class RRDBEngine(_LayerPlans):
         g, f = self.gen, self.nf
         ring = len(rdb_bufs)
         keep_all = ring > 3
+        self._keep_all = keep_all
         first = rdb_bufs[0]
         if keep_all:
             ops.conv_first(x, g.conv_first.weight, g.conv_first.bias, first, 0)

@@ -105,7 +105,8 @@ _TORCH_OPS = os.environ.get("XMM_TORCH_OPS", "0") == "1"
 _TORCH_FWD_KEYS = {"lrelu", "s0", "r1", "r1_coff", "s1", "r2", "r2_coff", "s2", "wblob_row", "tap_mode"}
 
 
-CHAIN_AUTO, CHAIN_PIPELINED, CHAIN_LAYER_BY_LAYER = 0, 1, 2
+CHAIN_AUTO, CHAIN_PIPELINED, CHAIN_LAYER_BY_LAYER, CHAIN_FUSED = 0, 1, 2, 3
+CHAIN_SKIP_DEAD_STORES = 0x100  # flag: outputs of layers 1..n-1 are not read after the call (inference)
 _chain_ws: dict = {}
 _chain_ws_retired: list = []  # outgrown workspaces stay allocated: a captured CUDA graph may still hold their address
 
@@ -113,8 +114,10 @@ _chain_ws_retired: list = []  # outgrown workspaces stay allocated: a captured C
 def conv3x3_chain(layers, mode: int = CHAIN_AUTO) -> None:
     """Dependent 3x3 convolutions (one dense block: forward convs or backward data gradients) through
     ``xmm_conv3x3_chain_bf16``.  ``layers``: list of (args, kwargs) exactly as for :func:`conv3x3`; the result equals
-    calling conv3x3 on them in order.  mode: CHAIN_AUTO / CHAIN_PIPELINED (one launch, layers pipelined over SM
-    groups) / CHAIN_LAYER_BY_LAYER."""
+    calling conv3x3 on them in order (up to fp32 summation order).  mode: CHAIN_AUTO (the fused dense-block kernels
+    where the layers qualify, else layer by layer) / CHAIN_PIPELINED (one launch, layers pipelined over SM groups) /
+    CHAIN_LAYER_BY_LAYER / CHAIN_FUSED (error if the layers are not a dense block), optionally
+    ``| CHAIN_SKIP_DEAD_STORES``."""
     n = len(layers)
     arr = (Conv3x3Params * n)()
     for p, (a, kw) in zip(arr, layers):
@@ -129,7 +132,7 @@ def conv3x3_chain(layers, mode: int = CHAIN_AUTO) -> None:
         ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
         _chain_ws[dev] = ws
     _lib.check(lib.xmm_conv3x3_chain_bf16(arr, n, int(mode), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
-    _count(1 if mode == CHAIN_PIPELINED else n)
+    _count(1 if (mode & 0xff) == CHAIN_PIPELINED else n)  # (the fused form is 2 launches; counted as its n layers)
 
 
 def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
