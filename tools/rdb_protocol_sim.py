@@ -25,7 +25,7 @@ class Bar:
 
 def simulate(nl, g, pieces, stages, verbose=False):
     ring = RINGS[nl]
-    full = [Bar(1, f"full{s}") for s in range(stages)]
+    full = [[Bar(1, f"full{l}.{s}") for s in range(8)] for l in range(nl)]
     empty = [Bar(1, f"empty{s}") for s in range(stages)]
     tfull = [[Bar(1, f"tfull{l}.{g}") for g in range(2)] for l in range(nl)]
     tdrain = [[Bar(4, f"tdrain{l}.{g}") for g in range(2)] for l in range(nl)]
@@ -37,37 +37,46 @@ def simulate(nl, g, pieces, stages, verbose=False):
 
     def producer():
         stage, phase = 0, 0
+        fills = [0] * nl
         for (rnd, l, p, r, flush, n, seq) in steps:
             if flush:
                 continue
             for _ in range(g):
                 while not empty[stage].ready(phase ^ 1):
                     yield ("empty", stage)
-                tma.append([3, full[stage]])
+                tma.append([3, full[l][fills[l] % 8]])
+                fills[l] += 1
                 stage += 1
                 if stage == stages:
                     stage, phase = 0, phase ^ 1
         return
 
-    def mma():
-        stage, phase = 0, 0
+    def mma(my_layer):
+        stage, fills = 0, 0
         cnt = [[0, 0] for _ in range(nl)]
         prev = [(0, 0)] * nl
         for task, (rnd, l, p, r, flush, n, seq) in enumerate(steps):
             pc = pieces[p]
             grp = task & 1
+            if l != my_layer:
+                if not flush:
+                    stage += g
+                    if stage >= stages:
+                        stage -= stages
+                continue
             if n > 0:
                 while not tdrain[l][prev[l][0]].ready(prev[l][1] & 1):
                     yield ("tdrain", l, n)
             if not flush:
                 for _ in range(g):
-                    while not full[stage].ready(phase):
-                        yield ("full", stage)
+                    while not full[l][fills % 8].ready((fills // 8) & 1):
+                        yield ("full", l, fills)
+                    fills += 1
                     pipe.append(("mma",))
                     pipe.append(("commit", empty[stage]))
                     stage += 1
                     if stage == stages:
-                        stage, phase = 0, phase ^ 1
+                        stage = 0
                 for m in range(nl - 1):
                     if m < l:
                         sq = seq[m] + (r - (pc["ra"] - (nl - 1 - m)))
@@ -109,7 +118,9 @@ def simulate(nl, g, pieces, stages, verbose=False):
                     mfull[l][slot].arrive()
         return
 
-    agents = {"producer": producer(), "mma": mma(), "epi0": epilogue(0), "epi1": epilogue(1)}
+    agents = {"producer": producer(), "epi0": epilogue(0), "epi1": epilogue(1)}
+    for l in range(nl):
+        agents[f"mma{l}"] = mma(l)
     blocked = {}
     ticks = 0
     while agents:

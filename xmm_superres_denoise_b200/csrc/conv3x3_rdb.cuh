@@ -49,7 +49,7 @@ constexpr int kRdbP = 63;                         // pixels of one band segment 
 constexpr int kRdbBoxPx = kRdbP + 2;              // segment + both halo pixels
 constexpr int kRdbTileData = 2 * kRdbBoxPx * 64;  // bytes one TMA box writes (32 bf16 channels per pixel)
 constexpr int kRdbTileBytes = 17 * 512;           // tile pitch: whole SWIZZLE_64B atoms
-constexpr int kRdbThreads = 320;                  // producer warp, issuer warp, 2 x 4 epilogue warps
+constexpr int kRdbThreads = 384;                  // producer warp, one issuer warp per layer (<= 3), 2 x 4 epilogue warps
 constexpr int kRdbSlots = 5;                      // accumulator slots per layer
 constexpr int kRdbSlotCols = kRdbSlots * 32;
 constexpr int kRdbMaxRing = 8;
@@ -79,6 +79,9 @@ struct RdbArgs {
   int r1_ctot, r1_coff;
   const __nv_bfloat16* r2;
   int r2_ctot, r2_coff;
+  int backoff_ns;   // nanosleep between polls of the producer / epilogue waits (0: none)
+  int prefetch_rows;  // the producer asks L2 for the global maps of the row this many steps ahead (0: off)
+  int multi_issue;  // 1: one issuer thread per layer (warps 1..NL); 0: warp 1 issues every layer
   long long* prof;  // optional (XMM_RDB_PROF=1): 16 cycle counters per CTA, see launch_rdb
 };
 
@@ -203,6 +206,16 @@ __device__ __forceinline__ void rdb_wait(uint64_t* bar, uint32_t parity, int tag
   }
 }
 
+// for the warps that are not on the critical path of the tensor pipe (producer, epilogue): back off between polls so
+// that the polling itself (a shared-memory access per try_wait, an issue slot per loop turn) does not compete with
+// the MMA operand reads and the working warps of the same scheduler
+__device__ __forceinline__ void rdb_wait_backoff(uint64_t* bar, uint32_t parity, int tag, int a, int b2, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+    if (++spins > (1u << 24)) rdb_wait_timeout(tag, a, b2, int(parity));
+  }
+}
 // the same, adding the cycles spent waiting to `acc` when profiling
 #ifndef XMM_RDB_PROFILE
 #define XMM_RDB_PROFILE 0  // 1: cycle counters of the issuer (XMM_RDB_PROF=1 prints them per launch)
@@ -228,6 +241,18 @@ __device__ __forceinline__ void tmem_st_zero32(uint32_t taddr) {
       "r"(z)
       : "memory");
 }
+// 32 lanes x 32 consecutive fp32 columns <- 32 registers per thread
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // G: feature maps read from global memory (x0 .. x_{G-1}); NL: fused layers.  Layer l (0-based) is conv_{G+l}: its K
@@ -248,8 +273,10 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
   constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};  // row tiles of the in-CTA maps (== args.ring0 / ring1, checked by the host)
   uint8_t* after = map_s[1] + size_t(NM > 1 ? args.ring1 : 0) * kRdbTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = full_bar + kRdbMaxStages;
+  // "chunk landed" barriers are per LAYER (ring of 8 each: a barrier has one waiter -- that layer's issuer -- which sees
+  // every phase); the stage tiles themselves are one ring shared by all layers, handed out in walk order
+  uint64_t* full_bar = bars;  // [NL][kRdbMaxStages]
+  uint64_t* empty_bar = full_bar + 3 * kRdbMaxStages;
   uint64_t* tfull_bar = empty_bar + kRdbMaxStages;  // [NL][2]: one per (layer, epilogue group that drains the row)
   uint64_t* tdrain_bar = tfull_bar + 6;             // [NL][2]
   uint64_t* mfull_bar = tdrain_bar + 6;             // [2][kRdbMaxRing]
@@ -262,10 +289,8 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_in);
-    for (int s = 0; s < args.stages; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < NL * kRdbMaxStages; ++s) ptx::mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < args.stages; ++s) ptx::mbar_init(&empty_bar[s], 1);
     for (int l = 0; l < 2 * NL; ++l) {
       ptx::mbar_init(&tfull_bar[l], 1);
       ptx::mbar_init(&tdrain_bar[l], 4);  // the four warps of the group that drained the row
@@ -284,17 +309,38 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  if (warp >= 2) {
-    // accumulators start at zero (every MMA accumulates); halo positions of the map tiles stay zero for ever
-    if (warp < 6) {
-      const uint32_t lane_base = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-      for (int s = 0; s < NL * kRdbSlots; ++s) tmem_st_zero32(lane_base + uint32_t(s * 32));
-      tmem_st_wait();
+  if (warp == 0 && ptx::elect_one()) {  // weights + biases of every layer (the accumulators are initialised from them)
+    uint32_t wtot = 0;
+    for (int l = 0; l < NL; ++l) wtot += args.layer[l].w_bytes + 128u;
+    ptx::mbar_expect_tx(w_bar, wtot);
+    for (int l = 0; l < NL; ++l) {
+      const uint8_t* gsrc = static_cast<const uint8_t*>(args.layer[l].wblob);
+      const uint32_t n_l = args.layer[l].w_bytes + 128u;
+      for (uint32_t off = 0; off < n_l; off += 32768u)
+        ptx::bulk_load(w_s + args.layer[l].smem_off + off, gsrc + off, n_l - off < 32768u ? n_l - off : 32768u, w_bar);
     }
+  }
+  if (warp >= 4) {
+    // halo positions of the map tiles stay zero for ever
     uint4* z = reinterpret_cast<uint4*>(map_s[0]);
     const int nz = (args.ring0 + (NM > 1 ? args.ring1 : 0)) * (kRdbTileBytes / 16);
-    for (int i = int(threadIdx.x) - 64; i < nz; i += kRdbThreads - 64) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = int(threadIdx.x) - 128; i < nz; i += kRdbThreads - 128) z[i] = make_uint4(0, 0, 0, 0);
     ptx::fence_proxy_async();
+    // Every MMA accumulates.  A row's accumulator (window slots 0..2) starts as the layer's BIAS, its carry slot
+    // (3, 4) as zero: the epilogue re-initialises a slot right after draining it and never adds the bias itself.
+    if (warp < 8) {
+      rdb_wait(w_bar, 0, 9, 0, 0);
+      const uint32_t lane_base = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+      for (int l = 0; l < NL; ++l) {
+        const float* bias_s = reinterpret_cast<const float*>(w_s + args.layer[l].smem_off + args.layer[l].w_bytes);
+        uint32_t b32[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) b32[k] = __float_as_uint(bias_s[k]);
+        for (int sl = 0; sl < 3; ++sl) tmem_st_32x32(lane_base + uint32_t(l * kRdbSlotCols + sl * 32), b32);
+        for (int sl = 3; sl < kRdbSlots; ++sl) tmem_st_zero32(lane_base + uint32_t(l * kRdbSlotCols + sl * 32));
+      }
+      tmem_st_wait();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -306,17 +352,11 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      uint32_t wtot = 0;
-      for (int l = 0; l < NL; ++l) wtot += args.layer[l].w_bytes + 128u;
-      ptx::mbar_expect_tx(w_bar, wtot);
-      for (int l = 0; l < NL; ++l) {
-        const uint8_t* gsrc = static_cast<const uint8_t*>(args.layer[l].wblob);
-        const uint32_t n_l = args.layer[l].w_bytes + 128u;
-        for (uint32_t off = 0; off < n_l; off += 32768u)
-          ptx::bulk_load(w_s + args.layer[l].smem_off + off, gsrc + off, n_l - off < 32768u ? n_l - off : 32768u, w_bar);
-      }
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t fills[NL];  // chunks loaded for layer l so far
+#pragma unroll
+      for (int l = 0; l < NL; ++l) fills[l] = 0;
       rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int, const int*) {
         if (flush) return;
         // input row r of both bands; above / below a band: the neighbouring band's rows (outside the image: zeros)
@@ -330,20 +370,46 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          rdb_wait(&empty_bar[stage], phase ^ 1u, 1, l, stage);
-          ptx::mbar_expect_tx(&full_bar[stage], kRdbTileData);
-          ptx::tma_load_5d(stage_s + size_t(stage) * kRdbTileBytes, &tmap_in, &full_bar[stage], args.cin_off + 32 * g,
-                           pc.x0 - 1, row, band0, pc.b);
+          rdb_wait_backoff(&empty_bar[stage], phase ^ 1u, 1, l, stage, uint32_t(args.backoff_ns));
+          uint64_t* fb = &full_bar[l * kRdbMaxStages + int(fills[l]++ & uint32_t(kRdbMaxStages - 1))];
+          ptx::mbar_expect_tx(fb, kRdbTileData);
+          ptx::tma_load_5d(stage_s + size_t(stage) * kRdbTileBytes, &tmap_in, fb, args.cin_off + 32 * g, pc.x0 - 1, row, band0,
+                           pc.b);
           if (++stage == args.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
+        // the first layer streams the global maps from HBM (the others re-read them out of L2 a few rows later): with
+        // few stages the TMA latency is exposed, so its rows are requested into L2 ahead of time
+        if (l == 0 && args.prefetch_rows > 0) {
+          const int rp = r + args.prefetch_rows;
+          if (rp <= pc.rb + (NL - 1)) {
+            int prow = rp, pband = 0;
+            if (rp < 0) {
+              prow = rp + args.band_h;
+              pband = -1;
+            } else if (rp >= args.band_h) {
+              prow = rp - args.band_h;
+              pband = 1;
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmap_in)),
+                           "r"(args.cin_off + 32 * g), "r"(pc.x0 - 1), "r"(prow), "r"(pband), "r"(pc.b)
+                           : "memory");
+          }
+        }
       });
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (ptx::elect_one()) {
+  } else if (warp <= 3) {
+    // ------------------------------------------------------------ MMA issuers: warp 1 + l issues layer l
+    // One thread per layer: each runs the whole walk but waits and issues only for its own layer's steps, so the
+    // per-step bookkeeping of one layer (~100 instructions of a single thread) overlaps the MMAs of the others.
+    // (One thread for all layers was issue-bound: the tensor pipe's queue drained during every step's set-up.)
+    const int my_layer = args.multi_issue ? warp - 1 : (warp == 1 ? -1 : NL);  // -1: all layers
+    if (my_layer < NL && ptx::elect_one()) {
       rdb_wait(w_bar, 0, 7, 0, 0);
       ptx::tc_fence_after();
       const uint64_t bdesc0 = ptx::umma_smem_desc(ptx::smem_u32(w_s), 16, 512, ptx::UMMA_SW64);
@@ -355,7 +421,9 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
       constexpr uint32_t kTap16 = uint32_t(kRdbTapBytes) >> 4;
       constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, 96, 0, 0);
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t fills[NL];  // chunks of layer l consumed so far (by this thread)
+#pragma unroll
+      for (int l = 0; l < NL; ++l) fills[l] = 0;
       auto issue6 = [&](uint32_t d, uint32_t a, uint32_t b) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
@@ -377,6 +445,13 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
       for (int l = 0; l < NL; ++l) prev_bar[l] = prev_par[l] = 0;
       rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int n, const int* seq) {
         const uint32_t pair = uint32_t(2 * l) + ((task++) & 1u);
+        if (my_layer >= 0 && l != my_layer) {  // another issuer's step: only the shared TMA stage ring moves on
+          if (!flush) {
+            stage += G;
+            if (stage >= args.stages) stage -= args.stages;
+          }
+          return;
+        }
         // the row completed by the layer's previous step is out of its accumulator slots
         if (n > 0) rdb_wait_p(&tdrain_bar[prev_bar[l]], prev_par[l], 2, l, n, prof, pw[0]);
         ptx::tc_fence_after();
@@ -385,14 +460,13 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
           const uint32_t b_l = b_lo0 + (args.layer[l].smem_off >> 4);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            rdb_wait_p(&full_bar[stage], phase, 3, l, stage, prof, pw[1]);
+            rdb_wait_p(&full_bar[l * kRdbMaxStages + int(fills[l] & uint32_t(kRdbMaxStages - 1))],
+                       (fills[l] / uint32_t(kRdbMaxStages)) & 1u, 3, l, stage, prof, pw[1]);
+            ++fills[l];
             ptx::tc_fence_after();
             issue6(d, a_lo0 + uint32_t(stage) * kTile16, b_l + uint32_t(g * 9) * kTap16);
             ptx::umma_commit(&empty_bar[stage]);
-            if (++stage == args.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+            if (++stage == args.stages) stage = 0;
           }
 #pragma unroll
           for (int m = 0; m < NM; ++m)
@@ -412,7 +486,7 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
         prev_par[l] = (use_par >> pair) & 1u;
         use_par ^= 1u << pair;
       });
-      if (XMM_RDB_PROFILE && prof) {
+      if (XMM_RDB_PROFILE && prof && my_layer <= 0) {
         long long* o = args.prof + size_t(blockIdx.x) * 16;
         o[0] = clock64() - t_begin;
         o[1] = pw[0];
@@ -424,7 +498,7 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
     // ------------------------------------------------------------ epilogue
     rdb_wait(w_bar, 0, 8, 0, 0);  // biases ride with the weights
     const int q = warp & 3;             // TMEM lane quarter this warp may read
-    const int group = (warp - 2) >> 2;  // takes every other completed row
+    const int group = (warp - 4) >> 2;  // takes every other completed row
     const int pos = q * 32 + lane + 1;  // pixel position of this lane in a row tile
     const int band = pos >= kRdbBoxPx ? 1 : 0;
     const int pl = band ? pos - (kRdbBoxPx + 1) : pos - 1;  // pixel within the band segment
@@ -434,6 +508,8 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
     const uint32_t pos_xor = uint32_t(pos >> 1) & 3u;
     const bool prof = XMM_RDB_PROFILE && args.prof != nullptr;
     long long pw[2] = {0, 0};
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+    long long tph = 0;
     long long ntask = 0;
     const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
     uint32_t task = 0;
@@ -464,12 +540,15 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
 #pragma unroll
         for (int k = 0; k < 4; ++k) res2[k] = __ldg(p + k);
       }
-      rdb_wait_p(&tfull_bar[2 * l + group], kth, 5, l, n, prof, pw[0]);
+      if (XMM_RDB_PROFILE) rdb_wait_p(&tfull_bar[2 * l + group], kth, 5, l, n, prof, pw[0]);
+      else rdb_wait_backoff(&tfull_bar[2 * l + group], kth, 5, l, n, uint32_t(args.backoff_ns));
       ++ntask;
+      if (XMM_RDB_PROFILE) tph = clock64();
       ptx::tc_fence_after();
       const int phi = rdb_phi(j);
       const uint32_t t_main = lane_base + uint32_t(l * kRdbSlotCols + phi * 32);
       const uint32_t t_carry = lane_base + uint32_t(l * kRdbSlotCols + (3 + phi) * 32);
+      const float* bias_s = reinterpret_cast<const float*>(w_s + args.layer[l].smem_off + args.layer[l].w_bytes);
       uint32_t accr[32];
       ptx::tmem_ld_32x32(t_main, accr);
       float v[32];
@@ -485,25 +564,32 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(accr[k]);
       }
-      tmem_st_zero32(t_main);
+      {  // the slot's next row starts from the bias
+        uint32_t b32[32];
+        const uint32_t bias_a = ptx::smem_u32(bias_s);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint4 b4;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b4.x), "=r"(b4.y), "=r"(b4.z), "=r"(b4.w) : "r"(bias_a + 16u * k));
+          b32[4 * k] = b4.x;
+          b32[4 * k + 1] = b4.y;
+          b32[4 * k + 2] = b4.z;
+          b32[4 * k + 3] = b4.w;
+        }
+        tmem_st_32x32(t_main, b32);
+      }
       tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tdrain_bar[2 * l + group]);
+      if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[0] += t - tph; tph = t; }
       if (!real) return;
 
-      const float* bias_s = reinterpret_cast<const float*>(w_s + args.layer[l].smem_off + args.layer[l].w_bytes);
       const float slope = args.layer[l].lrelu_slope;
+      if (slope != 1.f) {  // LeakyReLU, 0 < slope < 1: max(v, slope * v)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * k);
-        v[4 * k] += b4.x;
-        v[4 * k + 1] += b4.y;
-        v[4 * k + 2] += b4.z;
-        v[4 * k + 3] += b4.w;
+        for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], v[k] * slope);
       }
-#pragma unroll
-      for (int k = 0; k < 32; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * slope;
       if (last) {
         const float s0 = args.s0;
         if (s0 != 1.f) {
@@ -534,12 +620,14 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
       uint4 o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = pack8(v + 8 * k);
+      if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[1] += t - tph; tph = t; }
       if (l < NL - 1) {
         // the next layers' A operand: row j of map l, swizzled as a TMA load would have written it; zeros outside
         // the image (padding) and on the junk lanes
         const int sq = seq[l] + (j - (pc.ra - e));
         const int slot = sq % ring[l];
         rdb_wait_p(&mempty_bar[l * kRdbMaxRing + slot], (uint32_t(sq / ring[l]) & 1u) ^ 1u, 6, l, sq, prof, pw[1]);
+        if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[2] += t - tph; tph = t; }
         uint8_t* dst = map_s[l] + size_t(slot) * kRdbTileBytes + pos_off;
         const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -547,13 +635,26 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&mfull_bar[l * kRdbMaxRing + slot]);
+        if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[3] += t - tph; tph = t; }
       }
       if (args.layer[l].store && owned) {
         uint4* gp = reinterpret_cast<uint4*>(args.layer[l].out + pix * args.layer[l].out_ctot + args.layer[l].out_coff);
 #pragma unroll
         for (int k = 0; k < 4; ++k) gp[k] = o[k];
       }
+      if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[4] += t - tph; tph = t; }
     });
+    if (XMM_RDB_PROFILE && prof && q == 0 && lane == 0) {
+      long long* o = args.prof + size_t(blockIdx.x) * 16 + 4 + 4 * group;
+      o[0] = clock64() - t_begin;
+      o[1] = pw[0];
+      o[2] = pw[1];
+      o[3] = ntask;
+      if (group == 0) {
+        long long* o2 = args.prof + size_t(blockIdx.x) * 16 + 12;
+        o2[0] = ph[0]; o2[1] = ph[1]; o2[2] = ph[3]; o2[3] = ph[4];
+      }
+    }
   }
 
   ptx::tc_fence_before();

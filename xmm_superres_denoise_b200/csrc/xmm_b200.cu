@@ -774,7 +774,13 @@ int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo&
   a.s0 = pl.s0; a.s1 = pl.s1; a.s2 = pl.s2;
   a.r1 = static_cast<const __nv_bfloat16*>(pl.r1); a.r1_ctot = pl.r1_ctot; a.r1_coff = pl.r1_coff;
   a.r2 = static_cast<const __nv_bfloat16*>(pl.r2); a.r2_ctot = pl.r2_ctot; a.r2_coff = pl.r2_coff;
-  constexpr int kBarBytes = 512;
+  static const int issuers_env = env_int("XMM_RDB_MULTI_ISSUE", 1);
+  a.multi_issue = issuers_env ? 1 : 0;
+  static const int backoff_env = env_int("XMM_RDB_BACKOFF_NS", 0);
+  static const int prefetch_env = env_int("XMM_RDB_PREFETCH_ROWS", 0);
+  a.backoff_ns = backoff_env;
+  a.prefetch_rows = prefetch_env;
+  constexpr int kBarBytes = 1024;
   const long long room = (long long)dev.max_smem_optin - 1024 - kBarBytes - (long long)a.w_total;
   int tiles = int(room / kRdbTileBytes);
   a.ring0 = NL == 3 ? 5 : 3;
@@ -807,11 +813,12 @@ int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo&
     XMM_CUDA_OK(cudaStreamSynchronize(stream));
     std::vector<long long> h(size_t(grid) * 16);
     XMM_CUDA_OK(cudaMemcpy(h.data(), prof_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    static const char* names[12] = {"issuer total", "issuer wait drained", "issuer wait TMA", "issuer wait map row",
+    static const char* names[16] = {"issuer total", "issuer wait drained", "issuer wait TMA", "issuer wait map row",
                                     "epi0 total", "epi0 wait row complete", "epi0 wait map slot", "epi0 rows",
-                                    "epi1 total", "epi1 wait row complete", "epi1 wait map slot", "epi1 rows"};
+                                    "epi1 total", "epi1 wait row complete", "epi1 wait map slot", "epi1 rows",
+                                    "epi0 drain (ld+st+arrive)", "epi0 math+pack", "epi0 map write+fence+arrive", "epi0 global store"};
     fprintf(stderr, "conv3x3_rdb<%d,%d> grid %d stages %d:", G, NL, grid, a.stages);
-    for (int k = 0; k < 12; ++k) {
+    for (int k = 0; k < 16; ++k) {
       double sum = 0;
       for (int c = 0; c < grid; ++c) sum += double(h[size_t(c) * 16 + k]);
       fprintf(stderr, " %s %.0f;", names[k], sum / grid);
