@@ -10,10 +10,13 @@ from test_rdb_schedule import RINGS, cta_pieces, tiles_x, walk  # noqa: E402
 
 
 class Bar:
+    arrivals = 0  # all barriers: a tick in which anything arrived anywhere made progress
+
     def __init__(self, count, name):
         self.count, self.pending, self.phase, self.name = count, count, 0, name
 
     def arrive(self):
+        Bar.arrivals += 1
         self.pending -= 1
         if self.pending == 0:
             self.phase += 1
@@ -23,17 +26,37 @@ class Bar:
         return (self.phase & 1) != parity
 
 
+def layer_steps(pieces, nl, l):
+    """What issuer l / epilogue group l iterate: their own layer only -- pieces in order, rows top to bottom, two
+    flush steps per piece.  Yields (piece index, r, flush, n, seq[list: per map, of the piece's first row])."""
+    e = nl - 1 - l
+    n = 0
+    seq = [0] * nl
+    for p, pc in enumerate(pieces):
+        for r in range(pc["ra"] - e - 1, pc["rb"] + e + 3):
+            yield p, r, r > pc["rb"] + e, n, list(seq)
+            n += 1
+        for m in range(nl):
+            seq[m] += (pc["rb"] - pc["ra"]) + 2 * (nl - 1 - m)
+
+
 def simulate(nl, g, pieces, stages, verbose=False):
     ring = RINGS[nl]
-    full = [[Bar(1, f"full{l}.{s}") for s in range(8)] for l in range(nl)]
+    lfull = [[Bar(1, f"lfull{l}.{s}") for s in range(8)] for l in range(nl)]
+    lstage = [[None] * 8 for _ in range(nl)]
     empty = [Bar(1, f"empty{s}") for s in range(stages)]
-    tfull = [[Bar(1, f"tfull{l}.{g}") for g in range(2)] for l in range(nl)]
-    tdrain = [[Bar(4, f"tdrain{l}.{g}") for g in range(2)] for l in range(nl)]
+    tfull = [Bar(1, f"tfull{l}") for l in range(nl)]
+    tdrain = [Bar(4, f"tdrain{l}") for l in range(nl)]
     mfull = [[Bar(4, f"mfull{m}.{s}") for s in range(max(ring[m], 1))] for m in range(nl - 1)]
     mempty = [[Bar(1, f"mempty{m}.{s}") for s in range(max(ring[m], 1))] for m in range(nl - 1)]
-    pipe = deque()       # tensor pipe FIFO: ("mma",) or ("commit", bar)
-    tma = deque()        # in-flight loads: (ticks left, bar)
+    pipes = [deque() for _ in range(nl)]   # per issuing thread: its MMAs complete in order; a commit follows them
+    tma = deque()                          # in-flight loads: [ticks left, bar]
     steps = list(walk(pieces, nl))
+    # the per-layer iteration must be the walk restricted to the layer
+    for l in range(nl):
+        assert [(p, r, fl, n) for (_, ll, p, r, fl, n, _) in steps if ll == l] == [(p, r, fl, n) for (p, r, fl, n, _) in
+                                                                                 layer_steps(pieces, nl, l)]
+        assert [sq for (_, ll, p, r, fl, n, sq) in steps if ll == l] == [sq for (p, r, fl, n, sq) in layer_steps(pieces, nl, l)]
 
     def producer():
         stage, phase = 0, 0
@@ -44,69 +67,54 @@ def simulate(nl, g, pieces, stages, verbose=False):
             for _ in range(g):
                 while not empty[stage].ready(phase ^ 1):
                     yield ("empty", stage)
-                tma.append([3, full[l][fills[l] % 8]])
+                k = fills[l] % 8
                 fills[l] += 1
+                lstage[l][k] = stage
+                tma.append([3, lfull[l][k]])
                 stage += 1
                 if stage == stages:
                     stage, phase = 0, phase ^ 1
         return
 
-    def mma(my_layer):
-        stage, fills = 0, 0
-        cnt = [[0, 0] for _ in range(nl)]
-        prev = [(0, 0)] * nl
-        for task, (rnd, l, p, r, flush, n, seq) in enumerate(steps):
+    def issuer(l):
+        e = nl - 1 - l
+        fills = 0
+        for (p, r, flush, n, seq) in layer_steps(pieces, nl, l):
             pc = pieces[p]
-            grp = task & 1
-            if l != my_layer:
-                if not flush:
-                    stage += g
-                    if stage >= stages:
-                        stage -= stages
-                continue
             if n > 0:
-                while not tdrain[l][prev[l][0]].ready(prev[l][1] & 1):
+                while not tdrain[l].ready((n - 1) & 1):
                     yield ("tdrain", l, n)
             if not flush:
                 for _ in range(g):
-                    while not full[l][fills % 8].ready((fills // 8) & 1):
-                        yield ("full", l, fills)
+                    k = fills % 8
+                    while not lfull[l][k].ready((fills // 8) & 1):
+                        yield ("lfull", l, fills)
+                    st = lstage[l][k]
                     fills += 1
-                    pipe.append(("mma",))
-                    pipe.append(("commit", empty[stage]))
-                    stage += 1
-                    if stage == stages:
-                        stage = 0
+                    pipes[l].append(("mma",))
+                    pipes[l].append(("commit", empty[st]))
                 for m in range(nl - 1):
                     if m < l:
                         sq = seq[m] + (r - (pc["ra"] - (nl - 1 - m)))
                         slot = sq % ring[m]
                         while not mfull[m][slot].ready((sq // ring[m]) & 1):
                             yield ("mfull", m, sq)
-                        pipe.append(("mma",))
-                        e = nl - 1 - l
+                        pipes[l].append(("mma",))
                         if l == nl - 1 or r < pc["ra"] - e or r > pc["rb"] + e - 1:
-                            pipe.append(("commit", mempty[m][slot]))
-            pipe.append(("commit", tfull[l][grp]))
-            prev[l] = (grp, cnt[l][grp])
-            cnt[l][grp] += 1
+                            pipes[l].append(("commit", mempty[m][slot]))
+            pipes[l].append(("commit", tfull[l]))
         return
 
-    def epilogue(group):
-        cnt = [0] * nl
-        for task, (rnd, l, p, r, flush, n, seq) in enumerate(steps):
-            if (task & 1) != group:
-                continue
-            kth = cnt[l]
-            cnt[l] += 1
+    def epilogue(l):
+        e = nl - 1 - l
+        for (p, r, flush, n, seq) in layer_steps(pieces, nl, l):
             pc = pieces[p]
             j = r - 1
-            e = nl - 1 - l
             real = pc["ra"] - e <= j < pc["rb"] + e
-            while not tfull[l][group].ready(kth & 1):
+            while not tfull[l].ready(n & 1):
                 yield ("tfull", l, n)
             for _ in range(4):
-                tdrain[l][group].arrive()
+                tdrain[l].arrive()
             if not real:
                 continue
             if l < nl - 1:
@@ -118,13 +126,15 @@ def simulate(nl, g, pieces, stages, verbose=False):
                     mfull[l][slot].arrive()
         return
 
-    agents = {"producer": producer(), "epi0": epilogue(0), "epi1": epilogue(1)}
+    agents = {"producer": producer()}
     for l in range(nl):
-        agents[f"mma{l}"] = mma(l)
+        agents[f"issuer{l}"] = issuer(l)
+        agents[f"epi{l}"] = epilogue(l)
     blocked = {}
     ticks = 0
     while agents:
         progressed = False
+        seen = Bar.arrivals
         for name in list(agents):
             try:
                 blocked[name] = next(agents[name])
@@ -132,12 +142,12 @@ def simulate(nl, g, pieces, stages, verbose=False):
                 del agents[name]
                 blocked.pop(name, None)
                 progressed = True
-        # tensor pipe: one op per tick; TMA: count down
-        if pipe:
-            op = pipe.popleft()
-            if op[0] == "commit":
-                op[1].arrive()
-            progressed = True
+        for pipe in pipes:   # each thread's ops complete in its own order, one per tick
+            if pipe:
+                op = pipe.popleft()
+                if op[0] == "commit":
+                    op[1].arrive()
+                progressed = True
         for t in list(tma):
             t[0] -= 1
             if t[0] <= 0:
@@ -145,8 +155,8 @@ def simulate(nl, g, pieces, stages, verbose=False):
                 tma.remove(t)
             progressed = True
         ticks += 1
-        if not progressed and not pipe and not tma:
-            # agents that yield are blocked; if all are and nothing is in flight: deadlock
+        progressed = progressed or Bar.arrivals != seen
+        if not progressed and not any(pipes) and not tma:
             return False, dict(blocked)
         if ticks > 5_000_000:
             return False, {"timeout": dict(blocked)}

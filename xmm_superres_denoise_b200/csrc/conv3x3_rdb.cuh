@@ -49,7 +49,7 @@ constexpr int kRdbP = 63;                         // pixels of one band segment 
 constexpr int kRdbBoxPx = kRdbP + 2;              // segment + both halo pixels
 constexpr int kRdbTileData = 2 * kRdbBoxPx * 64;  // bytes one TMA box writes (32 bf16 channels per pixel)
 constexpr int kRdbTileBytes = 17 * 512;           // tile pitch: whole SWIZZLE_64B atoms
-constexpr int kRdbThreads = 384;                  // producer warp, one issuer warp per layer (<= 3), 2 x 4 epilogue warps
+constexpr int kRdbThreads = 512;                  // producer warp, one issuer warp + four epilogue warps per layer (<= 3)
 constexpr int kRdbSlots = 5;                      // accumulator slots per layer
 constexpr int kRdbSlotCols = kRdbSlots * 32;
 constexpr int kRdbMaxRing = 8;
@@ -255,281 +255,138 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// G: feature maps read from global memory (x0 .. x_{G-1}); NL: fused layers.  Layer l (0-based) is conv_{G+l}: its K
-// chunks are the G global maps then the l maps produced in this CTA.
-template <int G, int NL>
-__global__ void __launch_bounds__(kRdbThreads, 1)
-conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs args) {
-  static_assert(NL == 2 || NL == 3, "two or three fused layers");
-  static_assert(NL * kRdbSlotCols <= 512, "accumulators exceed TMEM");
-  constexpr int NM = NL - 1;  // in-CTA maps
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* w_s = smem;
-  uint8_t* stage_s = smem + args.w_total;
-  uint8_t* map_s[2];
-  map_s[0] = stage_s + size_t(args.stages) * kRdbTileBytes;
-  map_s[1] = map_s[0] + size_t(args.ring0) * kRdbTileBytes;
-  constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};  // row tiles of the in-CTA maps (== args.ring0 / ring1, checked by the host)
-  uint8_t* after = map_s[1] + size_t(NM > 1 ? args.ring1 : 0) * kRdbTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
-  // "chunk landed" barriers are per LAYER (ring of 8 each: a barrier has one waiter -- that layer's issuer -- which sees
-  // every phase); the stage tiles themselves are one ring shared by all layers, handed out in walk order
-  uint64_t* full_bar = bars;  // [NL][kRdbMaxStages]
-  uint64_t* empty_bar = full_bar + 3 * kRdbMaxStages;
-  uint64_t* tfull_bar = empty_bar + kRdbMaxStages;  // [NL][2]: one per (layer, epilogue group that drains the row)
-  uint64_t* tdrain_bar = tfull_bar + 6;             // [NL][2]
-  uint64_t* mfull_bar = tdrain_bar + 6;             // [2][kRdbMaxRing]
-  uint64_t* mempty_bar = mfull_bar + 2 * kRdbMaxRing;
-  uint64_t* w_bar = mempty_bar + 2 * kRdbMaxRing;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_bar + 1);
+// Shared-memory carve-up, identical in every thread.
+struct RdbCtx {
+  uint8_t* w_s;        // weights + biases of every layer
+  uint8_t* stage_s;    // TMA stages (one ring shared by all layers, handed out in walk order)
+  uint8_t* map_s[2];   // row tiles of the in-CTA maps
+  uint64_t* lfull;     // [NL][8] chunk k (mod 8) of layer l has landed        (waiter: issuer l)
+  uint64_t* empty;     // [stages] the MMAs that read the stage are done        (waiter: producer)
+  uint64_t* tfull;     // [NL] the row a step completes is in TMEM              (waiter: epilogue group l)
+  uint64_t* tdrain;    // [NL] ... has been drained and its slot re-initialised (waiter: issuer l)
+  uint64_t* mfull;     // [2][8] row tile of map m written                       (waiters: issuers m+1 ..)
+  uint64_t* mempty;    // [2][8] ... read by its last reader                     (waiter: epilogue group m)
+  uint64_t* w_bar;
+  volatile int* lstage;  // [NL][8] which stage holds chunk k (mod 8) of layer l (written by the producer)
+  uint32_t tmem_base;
+};
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmap_in);
-    for (int s = 0; s < NL * kRdbMaxStages; ++s) ptx::mbar_init(&full_bar[s], 1);
-    for (int s = 0; s < args.stages; ++s) ptx::mbar_init(&empty_bar[s], 1);
-    for (int l = 0; l < 2 * NL; ++l) {
-      ptx::mbar_init(&tfull_bar[l], 1);
-      ptx::mbar_init(&tdrain_bar[l], 4);  // the four warps of the group that drained the row
-    }
-    for (int m = 0; m < NM; ++m)
-      for (int s = 0; s < ring[m]; ++s) {
-        ptx::mbar_init(&mfull_bar[m * kRdbMaxRing + s], 4);
-        ptx::mbar_init(&mempty_bar[m * kRdbMaxRing + s], 1);  // the commit of the row's last reader
-      }
-    ptx::mbar_init(w_bar, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr_s);
-  ptx::tc_fence_before();
-  __syncthreads();
+// ---------------------------------------------------------------------------------------------------- MMA issuer
+// One thread per layer: the bookkeeping of one layer's step (~60 instructions of a single thread) overlaps the MMAs
+// of the other layers.  The thread walks its OWN layer only: pieces in order, rows top to bottom.
+template <int G, int NL, int L>
+__device__ __forceinline__ void rdb_issuer(const RdbArgs& args, const RdbCtx& c, const RdbSched<NL>& sched) {
+  constexpr int NM = NL - 1;
+  constexpr int e = NL - 1 - L;
+  constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};
+  rdb_wait(c.w_bar, 0, 7, L, 0);
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
-
-  if (warp == 0 && ptx::elect_one()) {  // weights + biases of every layer (the accumulators are initialised from them)
-    uint32_t wtot = 0;
-    for (int l = 0; l < NL; ++l) wtot += args.layer[l].w_bytes + 128u;
-    ptx::mbar_expect_tx(w_bar, wtot);
-    for (int l = 0; l < NL; ++l) {
-      const uint8_t* gsrc = static_cast<const uint8_t*>(args.layer[l].wblob);
-      const uint32_t n_l = args.layer[l].w_bytes + 128u;
-      for (uint32_t off = 0; off < n_l; off += 32768u)
-        ptx::bulk_load(w_s + args.layer[l].smem_off + off, gsrc + off, n_l - off < 32768u ? n_l - off : 32768u, w_bar);
-    }
-  }
-  if (warp >= 4) {
-    // halo positions of the map tiles stay zero for ever
-    uint4* z = reinterpret_cast<uint4*>(map_s[0]);
-    const int nz = (args.ring0 + (NM > 1 ? args.ring1 : 0)) * (kRdbTileBytes / 16);
-    for (int i = int(threadIdx.x) - 128; i < nz; i += kRdbThreads - 128) z[i] = make_uint4(0, 0, 0, 0);
-    ptx::fence_proxy_async();
-    // Every MMA accumulates.  A row's accumulator (window slots 0..2) starts as the layer's BIAS, its carry slot
-    // (3, 4) as zero: the epilogue re-initialises a slot right after draining it and never adds the bias itself.
-    if (warp < 8) {
-      rdb_wait(w_bar, 0, 9, 0, 0);
-      const uint32_t lane_base = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-      for (int l = 0; l < NL; ++l) {
-        const float* bias_s = reinterpret_cast<const float*>(w_s + args.layer[l].smem_off + args.layer[l].w_bytes);
-        uint32_t b32[32];
+  const uint64_t bdesc0 = ptx::umma_smem_desc(ptx::smem_u32(c.w_s), 16, 512, ptx::UMMA_SW64);
+  const uint64_t adesc0 = ptx::umma_smem_desc(ptx::smem_u32(c.stage_s), 16, 512, ptx::UMMA_SW64);
+  const uint32_t a_hi = uint32_t(adesc0 >> 32), b_hi = uint32_t(bdesc0 >> 32);
+  const uint32_t a_lo0 = uint32_t(adesc0);
+  const uint32_t b_l = uint32_t(bdesc0) + (args.layer[L].smem_off >> 4);
+  const uint32_t a_map0[2] = {a_lo0 + uint32_t((c.map_s[0] - c.stage_s) >> 4), a_lo0 + uint32_t((c.map_s[1] - c.stage_s) >> 4)};
+  constexpr uint32_t kTile16 = uint32_t(kRdbTileBytes) >> 4;
+  constexpr uint32_t kTap16 = uint32_t(kRdbTapBytes) >> 4;
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, 96, 0, 0);
+  auto issue6 = [&](uint32_t d, uint32_t a, uint32_t b) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) b32[k] = __float_as_uint(bias_s[k]);
-        for (int sl = 0; sl < 3; ++sl) tmem_st_32x32(lane_base + uint32_t(l * kRdbSlotCols + sl * 32), b32);
-        for (int sl = 3; sl < kRdbSlots; ++sl) tmem_st_zero32(lane_base + uint32_t(l * kRdbSlotCols + sl * 32));
-      }
-      tmem_st_wait();
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-
-  RdbSched<NL> sched;
-  sched.init(args);
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (ptx::elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t fills[NL];  // chunks loaded for layer l so far
+    for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-      for (int l = 0; l < NL; ++l) fills[l] = 0;
-      rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int, const int*) {
-        if (flush) return;
-        // input row r of both bands; above / below a band: the neighbouring band's rows (outside the image: zeros)
-        int row = r, band0 = 0;
-        if (r < 0) {
-          row = r + args.band_h;
-          band0 = -1;
-        } else if (r >= args.band_h) {
-          row = r - args.band_h;
-          band0 = 1;
-        }
+      for (int ks = 0; ks < 2; ++ks)
+        ptx::umma_ss_lh<true>(d, a + uint32_t((dx * 64 + ks * 32) >> 4), a_hi, b + uint32_t(dx * 3) * kTap16 + uint32_t((ks * 32) >> 4),
+                              b_hi, kIdesc);
+  };
+  const bool prof = XMM_RDB_PROFILE && args.prof != nullptr && L == 0;
+  long long pw[3] = {0, 0, 0};
+  const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
+  uint32_t fills = 0;  // chunks consumed so far
+  uint32_t n = 0;      // steps taken so far
+  int seq[2] = {0, 0}; // sequence number, in map m, of the current piece's first row
+  for (int pi = 0; pi < sched.npieces; ++pi) {
+    const RdbPiece pc = sched.get(pi);
+    const int r_last = pc.rb + e;  // last step with MMAs; two flush steps follow
+    for (int r = pc.ra - e - 1; r <= r_last + 2; ++r, ++n) {
+      // the row completed by the previous step is out of its accumulator slots (and they are re-initialised)
+      if (n > 0) rdb_wait_p(&c.tdrain[L], (n - 1u) & 1u, 2, L, int(n), prof, pw[0]);
+      ptx::tc_fence_after();
+      if (r <= r_last) {
+        const uint32_t d = c.tmem_base + uint32_t(L * kRdbSlotCols + rdb_phi(r - 1) * 32);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          rdb_wait_backoff(&empty_bar[stage], phase ^ 1u, 1, l, stage, uint32_t(args.backoff_ns));
-          uint64_t* fb = &full_bar[l * kRdbMaxStages + int(fills[l]++ & uint32_t(kRdbMaxStages - 1))];
-          ptx::mbar_expect_tx(fb, kRdbTileData);
-          ptx::tma_load_5d(stage_s + size_t(stage) * kRdbTileBytes, &tmap_in, fb, args.cin_off + 32 * g, pc.x0 - 1, row, band0,
-                           pc.b);
-          if (++stage == args.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          const int k = int(fills & 7u);
+          rdb_wait_p(&c.lfull[L * 8 + k], (fills >> 3) & 1u, 3, L, k, prof, pw[1]);
+          const int stage = c.lstage[L * 8 + k];
+          ++fills;
+          ptx::tc_fence_after();
+          issue6(d, a_lo0 + uint32_t(stage) * kTile16, b_l + uint32_t(g * 9) * kTap16);
+          ptx::umma_commit(&c.empty[stage]);
         }
-        // the first layer streams the global maps from HBM (the others re-read them out of L2 a few rows later): with
-        // few stages the TMA latency is exposed, so its rows are requested into L2 ahead of time
-        if (l == 0 && args.prefetch_rows > 0) {
-          const int rp = r + args.prefetch_rows;
-          if (rp <= pc.rb + (NL - 1)) {
-            int prow = rp, pband = 0;
-            if (rp < 0) {
-              prow = rp + args.band_h;
-              pband = -1;
-            } else if (rp >= args.band_h) {
-              prow = rp - args.band_h;
-              pband = 1;
-            }
 #pragma unroll
-            for (int g = 0; g < G; ++g)
-              asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
-                               reinterpret_cast<uint64_t>(&tmap_in)),
-                           "r"(args.cin_off + 32 * g), "r"(pc.x0 - 1), "r"(prow), "r"(pband), "r"(pc.b)
-                           : "memory");
-          }
-        }
-      });
-    }
-  } else if (warp <= 3) {
-    // ------------------------------------------------------------ MMA issuers: warp 1 + l issues layer l
-    // One thread per layer: each runs the whole walk but waits and issues only for its own layer's steps, so the
-    // per-step bookkeeping of one layer (~100 instructions of a single thread) overlaps the MMAs of the others.
-    // (One thread for all layers was issue-bound: the tensor pipe's queue drained during every step's set-up.)
-    const int my_layer = args.multi_issue ? warp - 1 : (warp == 1 ? -1 : NL);  // -1: all layers
-    if (my_layer < NL && ptx::elect_one()) {
-      rdb_wait(w_bar, 0, 7, 0, 0);
-      ptx::tc_fence_after();
-      const uint64_t bdesc0 = ptx::umma_smem_desc(ptx::smem_u32(w_s), 16, 512, ptx::UMMA_SW64);
-      const uint64_t adesc0 = ptx::umma_smem_desc(ptx::smem_u32(stage_s), 16, 512, ptx::UMMA_SW64);
-      const uint32_t a_hi = uint32_t(adesc0 >> 32), b_hi = uint32_t(bdesc0 >> 32);
-      const uint32_t a_lo0 = uint32_t(adesc0), b_lo0 = uint32_t(bdesc0);
-      const uint32_t a_map0[2] = {a_lo0 + uint32_t((map_s[0] - stage_s) >> 4), a_lo0 + uint32_t((map_s[1] - stage_s) >> 4)};
-      constexpr uint32_t kTile16 = uint32_t(kRdbTileBytes) >> 4;
-      constexpr uint32_t kTap16 = uint32_t(kRdbTapBytes) >> 4;
-      constexpr uint32_t kIdesc = ptx::umma_idesc_bf16_f32(128, 96, 0, 0);
-      int stage = 0;
-      uint32_t fills[NL];  // chunks of layer l consumed so far (by this thread)
-#pragma unroll
-      for (int l = 0; l < NL; ++l) fills[l] = 0;
-      auto issue6 = [&](uint32_t d, uint32_t a, uint32_t b) {
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            ptx::umma_ss_lh<true>(d, a + uint32_t((dx * 64 + ks * 32) >> 4), a_hi,
-                                  b + uint32_t(dx * 3) * kTap16 + uint32_t((ks * 32) >> 4), b_hi, kIdesc);
-      };
-      // Completed rows go to the two epilogue groups alternately (in walk order).  Every barrier has ONE waiter that
-      // sees each of its phases: (layer, group) pairs have their own "row complete" / "row drained" barriers, and
-      // the k-th use of a pair is phase k.
-      const bool prof = XMM_RDB_PROFILE && args.prof != nullptr;
-      long long pw[3] = {0, 0, 0};
-      const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
-      uint32_t task = 0;
-      uint32_t use_par = 0;  // bit 2l+g: parity of how often (layer l, group g) has been used
-      uint32_t prev_bar[NL], prev_par[NL];
-#pragma unroll
-      for (int l = 0; l < NL; ++l) prev_bar[l] = prev_par[l] = 0;
-      rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int n, const int* seq) {
-        const uint32_t pair = uint32_t(2 * l) + ((task++) & 1u);
-        if (my_layer >= 0 && l != my_layer) {  // another issuer's step: only the shared TMA stage ring moves on
-          if (!flush) {
-            stage += G;
-            if (stage >= args.stages) stage -= args.stages;
-          }
-          return;
-        }
-        // the row completed by the layer's previous step is out of its accumulator slots
-        if (n > 0) rdb_wait_p(&tdrain_bar[prev_bar[l]], prev_par[l], 2, l, n, prof, pw[0]);
-        ptx::tc_fence_after();
-        if (!flush) {
-          const uint32_t d = tmem_base + uint32_t(l * kRdbSlotCols + rdb_phi(r - 1) * 32);
-          const uint32_t b_l = b_lo0 + (args.layer[l].smem_off >> 4);
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            rdb_wait_p(&full_bar[l * kRdbMaxStages + int(fills[l] & uint32_t(kRdbMaxStages - 1))],
-                       (fills[l] / uint32_t(kRdbMaxStages)) & 1u, 3, l, stage, prof, pw[1]);
-            ++fills[l];
+        for (int m = 0; m < NM; ++m)
+          if (m < L) {
+            const int sq = seq[m] + (r - (pc.ra - (NL - 1 - m)));
+            const int slot = sq % ring[m];
+            rdb_wait_p(&c.mfull[m * 8 + slot], uint32_t(sq / ring[m]) & 1u, 4, L * 10 + m, sq, prof, pw[2]);
             ptx::tc_fence_after();
-            issue6(d, a_lo0 + uint32_t(stage) * kTile16, b_l + uint32_t(g * 9) * kTap16);
-            ptx::umma_commit(&empty_bar[stage]);
-            if (++stage == args.stages) stage = 0;
+            issue6(d, a_map0[m] + uint32_t(slot) * kTile16, b_l + uint32_t((G + m) * 9) * kTap16);
+            // the last layer that reads this row gives the tile back: layer L+1 reads rows [ra-e, rb+e-1]
+            if (L == NL - 1 || r < pc.ra - e || r > pc.rb + e - 1) ptx::umma_commit(&c.mempty[m * 8 + slot]);
           }
-#pragma unroll
-          for (int m = 0; m < NM; ++m)
-            if (m < l) {
-              const int sq = seq[m] + (r - (pc.ra - (NL - 1 - m)));
-              const int slot = sq % ring[m];
-              rdb_wait_p(&mfull_bar[m * kRdbMaxRing + slot], uint32_t(sq / ring[m]) & 1u, 4, l * 10 + m, sq, prof, pw[2]);
-              ptx::tc_fence_after();
-              issue6(d, a_map0[m] + uint32_t(slot) * kTile16, b_l + uint32_t((G + m) * 9) * kTap16);
-              // the last layer that reads this row gives the tile back: layer l+1 reads rows [ra-e, rb+e-1], e = NL-1-l
-              const int e = NL - 1 - l;
-              if (l == NL - 1 || r < pc.ra - e || r > pc.rb + e - 1) ptx::umma_commit(&mempty_bar[m * kRdbMaxRing + slot]);
-            }
-        }
-        ptx::umma_commit(&tfull_bar[pair]);  // row r-1 of layer l is complete
-        prev_bar[l] = pair;
-        prev_par[l] = (use_par >> pair) & 1u;
-        use_par ^= 1u << pair;
-      });
-      if (XMM_RDB_PROFILE && prof && my_layer <= 0) {
-        long long* o = args.prof + size_t(blockIdx.x) * 16;
-        o[0] = clock64() - t_begin;
-        o[1] = pw[0];
-        o[2] = pw[1];
-        o[3] = pw[2];
       }
+      ptx::umma_commit(&c.tfull[L]);  // row r-1 is complete
     }
-  } else {
-    // ------------------------------------------------------------ epilogue
-    rdb_wait(w_bar, 0, 8, 0, 0);  // biases ride with the weights
-    const int q = warp & 3;             // TMEM lane quarter this warp may read
-    const int group = (warp - 4) >> 2;  // takes every other completed row
-    const int pos = q * 32 + lane + 1;  // pixel position of this lane in a row tile
-    const int band = pos >= kRdbBoxPx ? 1 : 0;
-    const int pl = band ? pos - (kRdbBoxPx + 1) : pos - 1;  // pixel within the band segment
-    const bool lane_ok = band ? pl >= 0 : pl < kRdbP;
-    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
-    const uint32_t pos_off = uint32_t(pos) * 64u;
-    const uint32_t pos_xor = uint32_t(pos >> 1) & 3u;
-    const bool prof = XMM_RDB_PROFILE && args.prof != nullptr;
-    long long pw[2] = {0, 0};
-    long long ph[6] = {0, 0, 0, 0, 0, 0};
-    long long tph = 0;
-    long long ntask = 0;
-    const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
-    uint32_t task = 0;
-    uint32_t use_par = 0;  // bit l: parity of how many rows of layer l this group drained
-    rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int n, const int* seq) {
-      if (int((task++) & 1u) != group) return;
-      const uint32_t kth = (use_par >> l) & 1u;
-      use_par ^= 1u << l;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) seq[m] += (pc.rb - pc.ra) + 2 * (NL - 1 - m);
+  }
+  if (XMM_RDB_PROFILE && prof) {
+    long long* o = args.prof + size_t(blockIdx.x) * 16;
+    o[0] = clock64() - t_begin;
+    o[1] = pw[0];
+    o[2] = pw[1];
+    o[3] = pw[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- epilogue
+// Four warps per layer (one per TMEM lane quarter) drain that layer's rows in order.
+template <int G, int NL, int L>
+__device__ __forceinline__ void rdb_epilogue(const RdbArgs& args, const RdbCtx& c, const RdbSched<NL>& sched, int q, int lane) {
+  constexpr int e = NL - 1 - L;
+  constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};
+  constexpr bool last = L == NL - 1;
+  const int pos = q * 32 + lane + 1;  // pixel position of this lane in a row tile
+  const int band = pos >= kRdbBoxPx ? 1 : 0;
+  const int pl = band ? pos - (kRdbBoxPx + 1) : pos - 1;  // pixel within the band segment
+  const bool lane_ok = band ? pl >= 0 : pl < kRdbP;
+  const uint32_t lane_base = c.tmem_base + (uint32_t(q * 32) << 16) + uint32_t(L * kRdbSlotCols);
+  const uint32_t pos_off = uint32_t(pos) * 64u;
+  const uint32_t pos_xor = uint32_t(pos >> 1) & 3u;
+  const uint32_t bias_a = ptx::smem_u32(c.w_s + args.layer[L].smem_off + args.layer[L].w_bytes);
+  const float slope = args.layer[L].lrelu_slope;
+  const bool has_r1 = last && args.r1 != nullptr, has_r2 = last && args.r2 != nullptr;
+  const bool prof = XMM_RDB_PROFILE && args.prof != nullptr;
+  long long pw[2] = {0, 0};
+  long long ph[4] = {0, 0, 0, 0};
+  long long tph = 0;
+  const long long t_begin = XMM_RDB_PROFILE ? clock64() : 0;
+  uint32_t n = 0;  // rows drained so far
+  int seq = 0;     // sequence number, in map L, of the current piece's first row
+  for (int pi = 0; pi < sched.npieces; ++pi) {
+    const RdbPiece pc = sched.get(pi);
+    const int px = pc.x0 + pl;
+    const bool px_ok = lane_ok && px < args.width;
+    const bool px_own = px_ok && px >= pc.own_lo && px < pc.own_hi;
+    for (int r = pc.ra - e - 1; r <= pc.rb + e + 2; ++r, ++n) {
       const int j = r - 1;  // the row this step completed
-      const int e = NL - 1 - l;
       const bool real = j >= pc.ra - e && j < pc.rb + e;
-      const int px = pc.x0 + pl;
       const int y = band * args.band_h + j;
-      const bool inimg = lane_ok && px < args.width && y >= 0 && y < args.height;
-      const bool owned = real && inimg && px >= pc.own_lo && px < pc.own_hi && j >= pc.ra && j < pc.rb;
-      const size_t pix = (size_t(pc.b) * args.height + size_t(y < 0 ? 0 : y)) * args.width + size_t(px < 0 ? 0 : px);
+      const bool inimg = px_ok && y >= 0 && y < args.height;
+      const bool owned = real && px_own && inimg && j >= pc.ra && j < pc.rb;
+      const size_t pix = size_t((pc.b * args.height + (y < 0 ? 0 : y)) * args.width + (px_ok ? px : 0));
       // residuals of the last layer: requested before the accumulator is waited for
       uint4 res1[4], res2[4];
-      const bool last = l == NL - 1;
-      const bool has_r1 = last && args.r1 != nullptr, has_r2 = last && args.r2 != nullptr;
       if (has_r1 && owned) {
         const uint4* p = reinterpret_cast<const uint4*>(args.r1 + pix * args.r1_ctot + args.r1_coff);
 #pragma unroll
@@ -540,52 +397,52 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
 #pragma unroll
         for (int k = 0; k < 4; ++k) res2[k] = __ldg(p + k);
       }
-      if (XMM_RDB_PROFILE) rdb_wait_p(&tfull_bar[2 * l + group], kth, 5, l, n, prof, pw[0]);
-      else rdb_wait_backoff(&tfull_bar[2 * l + group], kth, 5, l, n, uint32_t(args.backoff_ns));
-      ++ntask;
+      if (XMM_RDB_PROFILE)
+        rdb_wait_p(&c.tfull[L], n & 1u, 5, L, int(n), prof, pw[0]);
+      else
+        rdb_wait_backoff(&c.tfull[L], n & 1u, 5, L, int(n), uint32_t(args.backoff_ns));
       if (XMM_RDB_PROFILE) tph = clock64();
       ptx::tc_fence_after();
       const int phi = rdb_phi(j);
-      const uint32_t t_main = lane_base + uint32_t(l * kRdbSlotCols + phi * 32);
-      const uint32_t t_carry = lane_base + uint32_t(l * kRdbSlotCols + (3 + phi) * 32);
-      const float* bias_s = reinterpret_cast<const float*>(w_s + args.layer[l].smem_off + args.layer[l].w_bytes);
-      uint32_t accr[32];
-      ptx::tmem_ld_32x32(t_main, accr);
+      const uint32_t t_main = lane_base + uint32_t(phi * 32);
+      const uint32_t t_carry = lane_base + uint32_t((3 + phi) * 32);
       float v[32];
-      if (phi < 2) {  // the row's first partial sums were collected in a carry slot
-        uint32_t car[32];
-        ptx::tmem_ld_32x32(t_carry, car);
-        ptx::tmem_ld_wait();
+      {
+        uint32_t accr[32];
+        ptx::tmem_ld_32x32(t_main, accr);
+        if (phi < 2) {  // the row's first partial sums were collected in a carry slot
+          uint32_t car[32];
+          ptx::tmem_ld_32x32(t_carry, car);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(car[k]) + __uint_as_float(accr[k]);
-        tmem_st_zero32(t_carry);
-      } else {
-        ptx::tmem_ld_wait();
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(car[k]) + __uint_as_float(accr[k]);
+          tmem_st_zero32(t_carry);
+        } else {
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(accr[k]);
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(accr[k]);
+        }
       }
       {  // the slot's next row starts from the bias
         uint32_t b32[32];
-        const uint32_t bias_a = ptx::smem_u32(bias_s);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          uint4 b4;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b4.x), "=r"(b4.y), "=r"(b4.z), "=r"(b4.w) : "r"(bias_a + 16u * k));
-          b32[4 * k] = b4.x;
-          b32[4 * k + 1] = b4.y;
-          b32[4 * k + 2] = b4.z;
-          b32[4 * k + 3] = b4.w;
-        }
+        for (int k = 0; k < 8; ++k)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b32[4 * k]), "=r"(b32[4 * k + 1]), "=r"(b32[4 * k + 2]), "=r"(b32[4 * k + 3])
+                       : "r"(bias_a + 16u * k));
         tmem_st_32x32(t_main, b32);
       }
       tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tdrain_bar[2 * l + group]);
-      if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[0] += t - tph; tph = t; }
-      if (!real) return;
+      if (lane == 0) ptx::mbar_arrive(&c.tdrain[L]);
+      if (XMM_RDB_PROFILE) {
+        const long long t = clock64();
+        ph[0] += t - tph;
+        tph = t;
+      }
+      if (!real) continue;
 
-      const float slope = args.layer[l].lrelu_slope;
       if (slope != 1.f) {  // LeakyReLU, 0 < slope < 1: max(v, slope * v)
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], v[k] * slope);
@@ -620,40 +477,223 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
       uint4 o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = pack8(v + 8 * k);
-      if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[1] += t - tph; tph = t; }
-      if (l < NL - 1) {
-        // the next layers' A operand: row j of map l, swizzled as a TMA load would have written it; zeros outside
+      if (XMM_RDB_PROFILE) {
+        const long long t = clock64();
+        ph[1] += t - tph;
+        tph = t;
+      }
+      if (!last) {
+        // the next layers' A operand: row j of map L, swizzled as a TMA load would have written it; zeros outside
         // the image (padding) and on the junk lanes
-        const int sq = seq[l] + (j - (pc.ra - e));
-        const int slot = sq % ring[l];
-        rdb_wait_p(&mempty_bar[l * kRdbMaxRing + slot], (uint32_t(sq / ring[l]) & 1u) ^ 1u, 6, l, sq, prof, pw[1]);
-        if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[2] += t - tph; tph = t; }
-        uint8_t* dst = map_s[l] + size_t(slot) * kRdbTileBytes + pos_off;
+        const int sq = seq + (j - (pc.ra - e));
+        const int slot = sq % ring[L];
+        rdb_wait_p(&c.mempty[L * 8 + slot], (uint32_t(sq / ring[L]) & 1u) ^ 1u, 6, L, sq, prof, pw[1]);
+        if (XMM_RDB_PROFILE) tph = clock64();
+        uint8_t* dst = c.map_s[L] + size_t(slot) * kRdbTileBytes + pos_off;
         const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + ((uint32_t(k) ^ pos_xor) << 4)) = inimg ? o[k] : zero;
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&mfull_bar[l * kRdbMaxRing + slot]);
-        if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[3] += t - tph; tph = t; }
+        if (lane == 0) ptx::mbar_arrive(&c.mfull[L * 8 + slot]);
+        if (XMM_RDB_PROFILE) {
+          const long long t = clock64();
+          ph[2] += t - tph;
+          tph = t;
+        }
       }
-      if (args.layer[l].store && owned) {
-        uint4* gp = reinterpret_cast<uint4*>(args.layer[l].out + pix * args.layer[l].out_ctot + args.layer[l].out_coff);
+      if (args.layer[L].store && owned) {
+        uint4* gp = reinterpret_cast<uint4*>(args.layer[L].out + pix * args.layer[L].out_ctot + args.layer[L].out_coff);
 #pragma unroll
         for (int k = 0; k < 4; ++k) gp[k] = o[k];
       }
-      if (XMM_RDB_PROFILE) { const long long t = clock64(); ph[4] += t - tph; tph = t; }
-    });
-    if (XMM_RDB_PROFILE && prof && q == 0 && lane == 0) {
-      long long* o = args.prof + size_t(blockIdx.x) * 16 + 4 + 4 * group;
-      o[0] = clock64() - t_begin;
-      o[1] = pw[0];
-      o[2] = pw[1];
-      o[3] = ntask;
-      if (group == 0) {
-        long long* o2 = args.prof + size_t(blockIdx.x) * 16 + 12;
-        o2[0] = ph[0]; o2[1] = ph[1]; o2[2] = ph[3]; o2[3] = ph[4];
+      if (XMM_RDB_PROFILE) {
+        const long long t = clock64();
+        ph[3] += t - tph;
+        tph = t;
       }
+    }
+    seq += (pc.rb - pc.ra) + 2 * e;
+  }
+  if (XMM_RDB_PROFILE && prof && q == 0 && lane == 0 && L < 2) {
+    long long* o = args.prof + size_t(blockIdx.x) * 16 + 4 + 4 * L;
+    o[0] = clock64() - t_begin;
+    o[1] = pw[0];
+    o[2] = pw[1];
+    o[3] = (long long)n;
+    if (L == 0) {
+      long long* o2 = args.prof + size_t(blockIdx.x) * 16 + 12;
+      o2[0] = ph[0];
+      o2[1] = ph[1];
+      o2[2] = ph[2];
+      o2[3] = ph[3];
+    }
+  }
+}
+
+// G: feature maps read from global memory (x0 .. x_{G-1}); NL: fused layers.  Layer l (0-based) is conv_{G+l}: its K
+// chunks are the G global maps then the l maps produced in this CTA.
+// Warp roles (512 threads): warp 0 = TMA producer (the only role that follows the interleaved walk: it decides the
+// order in which the layers' rows are loaded), warp 1 + l = MMA issuer of layer l, warps 4 + 4 l .. 7 + 4 l = epilogue
+// of layer l.  Issuers and epilogue groups only know their own layer; everything between roles is an mbarrier.
+template <int G, int NL>
+__global__ void __launch_bounds__(kRdbThreads, 1)
+conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs args) {
+  static_assert(NL == 2 || NL == 3, "two or three fused layers");
+  static_assert(NL * kRdbSlotCols <= 512, "accumulators exceed TMEM");
+  constexpr int NM = NL - 1;  // in-CTA maps
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  RdbCtx c;
+  c.w_s = smem;
+  c.stage_s = smem + args.w_total;
+  c.map_s[0] = c.stage_s + size_t(args.stages) * kRdbTileBytes;
+  c.map_s[1] = c.map_s[0] + size_t(args.ring0) * kRdbTileBytes;
+  uint8_t* after = c.map_s[1] + size_t(NM > 1 ? args.ring1 : 0) * kRdbTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after);
+  c.lfull = bars;            // 24
+  c.empty = c.lfull + 24;    // 8
+  c.tfull = c.empty + 8;     // 3
+  c.tdrain = c.tfull + 3;    // 3
+  c.mfull = c.tdrain + 3;    // 16
+  c.mempty = c.mfull + 16;   // 16
+  c.w_bar = c.mempty + 16;   // 1
+  c.lstage = reinterpret_cast<volatile int*>(c.w_bar + 1);  // 24 ints
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(const_cast<int*>(c.lstage) + 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_in);
+    for (int s = 0; s < NL * 8; ++s) ptx::mbar_init(&c.lfull[s], 1);
+    for (int s = 0; s < args.stages; ++s) ptx::mbar_init(&c.empty[s], 1);
+    for (int l = 0; l < NL; ++l) {
+      ptx::mbar_init(&c.tfull[l], 1);
+      ptx::mbar_init(&c.tdrain[l], 4);  // the four warps of the layer's epilogue group
+    }
+    for (int s = 0; s < 16; ++s) {
+      ptx::mbar_init(&c.mfull[s], 4);
+      ptx::mbar_init(&c.mempty[s], 1);  // the commit of the row's last reader
+    }
+    ptx::mbar_init(c.w_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_ptr_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  c.tmem_base = *tmem_ptr_s;
+
+  if (warp == 0 && ptx::elect_one()) {  // weights + biases of every layer (the accumulators are initialised from them)
+    uint32_t wtot = 0;
+    for (int l = 0; l < NL; ++l) wtot += args.layer[l].w_bytes + 128u;
+    ptx::mbar_expect_tx(c.w_bar, wtot);
+    for (int l = 0; l < NL; ++l) {
+      const uint8_t* gsrc = static_cast<const uint8_t*>(args.layer[l].wblob);
+      const uint32_t n_l = args.layer[l].w_bytes + 128u;
+      for (uint32_t off = 0; off < n_l; off += 32768u)
+        ptx::bulk_load(c.w_s + args.layer[l].smem_off + off, gsrc + off, n_l - off < 32768u ? n_l - off : 32768u, c.w_bar);
+    }
+  }
+  const int egroup = (warp - 4) >> 2;  // epilogue group = layer (warps 4..)
+  if (warp >= 4) {
+    // halo positions of the map tiles stay zero for ever
+    uint4* z = reinterpret_cast<uint4*>(c.map_s[0]);
+    const int nz = (args.ring0 + (NM > 1 ? args.ring1 : 0)) * (kRdbTileBytes / 16);
+    for (int i = int(threadIdx.x) - 128; i < nz; i += kRdbThreads - 128) z[i] = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+    // Every MMA accumulates.  A row's accumulator (window slots 0..2) starts as the layer's BIAS, its carry slot
+    // (3, 4) as zero: the epilogue re-initialises a slot right after draining it and never adds the bias itself.
+    if (egroup < NL) {
+      rdb_wait(c.w_bar, 0, 9, 0, 0);
+      const uint32_t lane_base = c.tmem_base + (uint32_t((warp & 3) * 32) << 16) + uint32_t(egroup * kRdbSlotCols);
+      const float* bias_s = reinterpret_cast<const float*>(c.w_s + args.layer[egroup].smem_off + args.layer[egroup].w_bytes);
+      uint32_t b32[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) b32[k] = __float_as_uint(bias_s[k]);
+      for (int sl = 0; sl < 3; ++sl) tmem_st_32x32(lane_base + uint32_t(sl * 32), b32);
+      for (int sl = 3; sl < kRdbSlots; ++sl) tmem_st_zero32(lane_base + uint32_t(sl * 32));
+      tmem_st_wait();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  RdbSched<NL> sched;
+  sched.init(args);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t fills[NL];  // chunks loaded for layer l so far
+#pragma unroll
+      for (int l = 0; l < NL; ++l) fills[l] = 0;
+      rdb_walk<NL>(sched, [&](int l, const RdbPiece& pc, int r, bool flush, int, const int*) {
+        if (flush) return;
+        // input row r of both bands; above / below a band: the neighbouring band's rows (outside the image: zeros)
+        int row = r, band0 = 0;
+        if (r < 0) {
+          row = r + args.band_h;
+          band0 = -1;
+        } else if (r >= args.band_h) {
+          row = r - args.band_h;
+          band0 = 1;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          rdb_wait_backoff(&c.empty[stage], phase ^ 1u, 1, l, stage, uint32_t(args.backoff_ns));
+          const int k = int(fills[l]++ & 7u);
+          c.lstage[l * 8 + k] = stage;  // (made visible to the issuer by the release of the arrive below)
+          uint64_t* fb = &c.lfull[l * 8 + k];
+          ptx::mbar_expect_tx(fb, kRdbTileData);
+          ptx::tma_load_5d(c.stage_s + size_t(stage) * kRdbTileBytes, &tmap_in, fb, args.cin_off + 32 * g, pc.x0 - 1, row, band0,
+                           pc.b);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        // the first layer streams the global maps from HBM (the others re-read them out of L2 a few rows later): with
+        // few stages the TMA latency is exposed, so its rows can be requested into L2 ahead of time
+        if (l == 0 && args.prefetch_rows > 0) {
+          const int rp = r + args.prefetch_rows;
+          if (rp <= pc.rb + (NL - 1)) {
+            int prow = rp, pband = 0;
+            if (rp < 0) {
+              prow = rp + args.band_h;
+              pband = -1;
+            } else if (rp >= args.band_h) {
+              prow = rp - args.band_h;
+              pband = 1;
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmap_in)),
+                           "r"(args.cin_off + 32 * g), "r"(pc.x0 - 1), "r"(prow), "r"(pband), "r"(pc.b)
+                           : "memory");
+          }
+        }
+      });
+    }
+  } else if (warp <= 3) {
+    if (warp - 1 < NL && ptx::elect_one()) {
+      if (warp == 1) rdb_issuer<G, NL, 0>(args, c, sched);
+      if (warp == 2) rdb_issuer<G, NL, 1>(args, c, sched);
+      if constexpr (NL == 3) {
+        if (warp == 3) rdb_issuer<G, NL, 2>(args, c, sched);
+      }
+    }
+  } else if (egroup < NL) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    if (egroup == 0) rdb_epilogue<G, NL, 0>(args, c, sched, q, lane);
+    if (egroup == 1) rdb_epilogue<G, NL, 1>(args, c, sched, q, lane);
+    if constexpr (NL == 3) {
+      if (egroup == 2) rdb_epilogue<G, NL, 2>(args, c, sched, q, lane);
     }
   }
 
@@ -661,7 +701,7 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
+    ptx::tmem_dealloc<512>(c.tmem_base);
   }
 }
 
