@@ -48,9 +48,10 @@ def peaks():
 
 
 def traffic_from_profile(batch: int):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/
-    r01_traffic.json: bytes per launch of conv3x3_dx_kernel<32,32> with cin=160, scaled linearly in the batch)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """STATIC figure, not measured in this run: DRAM bytes of the dominant kernels from the committed `ncu --set full`
+    capture (profiles/r02_traffic.json: dram__bytes_read + write of conv3x3_rdb_kernel<1,3> + <4,2> = one dense block at
+    batch 64, from profiles/r02_ncu_rdb_v5_summary.csv), scaled linearly in the batch.  Labelled as such in the line."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
@@ -411,7 +412,7 @@ def main() -> None:
         flop = 0.0
         for (inp, _coff, cin, _w, _kc, cout, _out, _ocoff), _kw in layers:
             flop += 2.0 * 9 * cin * cout * inp.shape[0] * inp.shape[1] * inp.shape[2]
-        prof_events.append((e0, e1, flop, 1 if mode == ops.CHAIN_PIPELINED else len(layers)))
+        prof_events.append((e0, e1, flop, ops.LAST_CHAIN_LAUNCHES))
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -522,8 +523,9 @@ def main() -> None:
                 "h2d_bytes_per_step": counts_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor",
-                     "kernel": "dense-block 3x3 convs: conv3x3_dx_kernel<32,32> (cin 64..160) + conv3x3_tc_kernel<32,32> "
-                               "(cin 32), timed per block of 5 launches",
+                     "kernel": "dense-block 3x3 convs: conv3x3_rdb_kernel<1,3> (conv1-3 fused) + conv3x3_rdb_kernel<4,2> "
+                               "(conv4-5 fused), timed per dense block (2 launches); layer-by-layer kernels where the "
+                               "fused form does not qualify",
                      "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_sustained"], "frac_of_burst": achieved / pk["bf16_burst"],
                      "peak_src": pk["src"] + " bf16_tflops_sustained (kernel timed inside a long step)",

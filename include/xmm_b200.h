@@ -139,6 +139,8 @@ int xmm_conv3x3_bf16(const xmm_conv3x3_params* p, void* stream);
 size_t xmm_conv3x3_chain_workspace_bytes(int nlayers, int batch, int height);
 int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode_flags, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* Kernels the calling thread's last xmm_conv3x3_chain_bf16 launched (2 fused, 1 pipelined, nlayers layer by layer). */
+int xmm_last_chain_launches(void);
 
 /* Input transforms ------------------------------------------------------------------- */
 #define XMM_STRETCH_LINEAR 0

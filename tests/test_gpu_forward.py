@@ -627,7 +627,7 @@ def test_generator_64_filters_matches_oracle(dev, kind, seed):
     seeds are ones whose random-init output is an image (0.1 % / 24 % of the pixels clamped), see the next test."""
     got, want, r = _f64_case(dev, kind, seed)
     assert r < REL_L2_BF16
-    assert psnr_db(got, want) > 80.0
+    assert psnr_db(got, want) > 65.0  # (an image of rms 0.05-0.08 at 5e-3 relative error sits at 70-72 dB)
 
 
 @pytest.mark.xfail(strict=False, reason="degenerate random init: 96.8 % of the fp32 output is clamped to 0 (rms 0.0034), and "

@@ -138,6 +138,7 @@ SIGNATURES = {
     "xmm_pack_weights": (c_int, [c_void_p, c_int, c_void_p]),
     "xmm_conv3x3_bf16": (c_int, [POINTER(Conv3x3Params), c_void_p]),
     "xmm_conv3x3_chain_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "xmm_last_chain_launches": (c_int, []),
     "xmm_conv3x3_chain_bf16": (c_int, [POINTER(Conv3x3Params), c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "xmm_normalize": (c_int, [POINTER(NormalizeParams), c_void_p]),
     "xmm_denormalize": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_int, c_int, c_void_p]),

@@ -43,7 +43,12 @@ constexpr int kRowPx = 8;
 constexpr int kRowPitch = kRowPx + 2;
 constexpr int kRowEpiWarps = 8;
 constexpr int kRowThreads = 64 + 32 * kRowEpiWarps;
-constexpr int kRowSideStages = 3;
+// EVEN, like the accumulator slots: output rows alternate between the two epilogue groups, so with an even ring every
+// stage is always waited for by the SAME group, which therefore sees each of the barrier's phases.  (With 3 stages a
+// group saw every other phase of a stage's "landed" barrier: a parity wait two phases ahead passes at once, the
+// group read the side tile before it had landed and released it early -- wrong residuals / masks or a wedged
+// pipeline, depending on timing; found with the protocol simulator of the fused kernels, tools/rdb_protocol_sim.py.)
+constexpr int kRowSideStages = 4;  // NT = 32; the 64-filter instantiation takes 2 (RowCfg::kSideStages)
 constexpr int kRowMaxSlots = 16;
 
 // compile-time epilogue variants (the launcher picks the instantiation; see row_epilogue_math)
@@ -59,6 +64,7 @@ struct RowCfg {
   static constexpr int kKSteps = KC / 16;
   static constexpr int kTapBytes = NT * kRowB;
   static constexpr int kSlots = 512 / NT;  // accumulator slots (one output row each)
+  static constexpr int kSideStages = NT == 32 ? kRowSideStages : 2;  // even (see kRowSideStages); 16 KB tiles at NT = 64
   static constexpr int kBiasBytes = NT * 4;
   static constexpr int kWarpOutBytes = 32 * NT * 2;  // [4 bands][8 px] x NT bf16, swizzled
   static constexpr int kOutBytes = kRowEpiWarps * kWarpOutBytes;
@@ -67,7 +73,7 @@ struct RowCfg {
   static constexpr int kBarBytes = (2 * kMaxStages + 2 * kRowMaxSlots + 1 + 2 * kRowSideStages) * 8 + 16;
   static size_t smem_bytes(uint32_t w_bytes, int stages, int nside) {
     return 1024 + ((size_t(w_bytes) + kBiasBytes + 1023) & ~size_t(1023)) + size_t(stages) * kStageBytes + kOutBytes +
-           size_t(kRowSideStages * nside) * kSideTileBytes + kBarBytes;
+           size_t(kSideStages * nside) * kSideTileBytes + kBarBytes;
   }
 };
 
@@ -210,7 +216,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   uint8_t* out_s = stage_s + size_t(args.stages) * Cfg::kStageBytes;
   uint8_t* side_s = out_s + Cfg::kOutBytes;
   const int nside = __popc(args.side_mask);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(side_s + size_t(kRowSideStages * nside) * Cfg::kSideTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_s + size_t(Cfg::kSideStages * nside) * Cfg::kSideTileBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
@@ -235,7 +241,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
       ptx::mbar_init(&tempty_bar[a], 4);  // the four warps of the group that drains this slot
     }
     ptx::mbar_init(w_bar, 1);
-    for (int a = 0; a < kRowSideStages; ++a) {
+    for (int a = 0; a < Cfg::kSideStages; ++a) {
       ptx::mbar_init(&sfull_bar[a], 1);
       ptx::mbar_init(&sempty_bar[a], 4);
     }
@@ -299,7 +305,7 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
                 ptx::tma_load_5d(dst, &side_maps.m[k], &sfull_bar[sst], coff[k], xt * kRowPx, r - 1, 0, b);
                 dst += Cfg::kSideTileBytes;
               }
-            if (++sst == kRowSideStages) {
+            if (++sst == Cfg::kSideStages) {
               sst = 0;
               sphase ^= 1u;
             }
@@ -414,10 +420,10 @@ conv3x3_row_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         ptx::mbar_wait(&tfull_bar[slot], uint32_t(v >> kSlotShift) & 1u);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(slot * NT);
-        const int sst = v % kRowSideStages;
+        const int sst = v % Cfg::kSideStages;
         const uint8_t* side[3] = {nullptr, nullptr, nullptr};
         if (EPI & (kRowMask | kRowR1 | kRowR2)) {
-          ptx::mbar_wait(&sfull_bar[sst], uint32_t(v / kRowSideStages) & 1u);
+          ptx::mbar_wait(&sfull_bar[sst], uint32_t(v / Cfg::kSideStages) & 1u);
           const uint8_t* src = side_s + size_t(sst * nside) * Cfg::kSideTileBytes;
 #pragma unroll
           for (int k = 0; k < 3; ++k)

@@ -515,10 +515,14 @@ extern "C" int xmm_conv3x3_bf16(const xmm_conv3x3_params* pp, void* stream) {
   rc = check_conv_params(p);
   if (rc != XMM_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // Row-hop form (conv3x3_row.cuh): the default wherever it qualifies (tap_mode 0 with a row-hop weight image);
-  // tap_mode 9 forces it; XMM_ROW=0 switches it off (A/B runs).
+  // Row-hop form (conv3x3_row.cuh): the default for the NARROW layers it qualifies for (tap_mode 0 with a row-hop
+  // weight image and cin <= 64 * kc / 32).  Measured at batch 64, 416x416 (tools/row_probe.py, profiles/
+  // r02_row_probe.log): cin 32 0.378 vs 0.426 ms (tap views), cin 64 0.565 vs 0.592 ms (column scatter); from cin 96
+  // on its 10/8 column halo costs more HBM traffic than its cheap epilogue saves (cin 160: 1.12 vs 0.92 ms).
+  // tap_mode 9 forces it; XMM_ROW=0 switches it off, XMM_ROW=2 lifts the cin limit (A/B runs).
   static const int row_env = [] { const char* e = getenv("XMM_ROW"); return e ? atoi(e) : 1; }();
-  if ((p.tap_mode <= 0 && row_env && p.wblob_row != nullptr) || p.tap_mode == 9) {
+  const bool row_narrow = p.cin <= 2 * p.kc || row_env == 2;
+  if ((p.tap_mode <= 0 && row_env && row_narrow && p.wblob_row != nullptr) || p.tap_mode == 9) {
     const char* why = "cout must equal kc (32 or 64)";
     int stages = 0;
     if (p.kc == 32 && p.cout == 32) {
@@ -742,6 +746,7 @@ const char* rdb_blocker(const xmm_conv3x3_params* L, int n, const DeviceInfo& de
         return "the last layer may not overwrite the block's own feature maps";
     }
   }
+  if ((long long)p0.batch * p0.height * p0.width >= (1LL << 31)) return "more than 2^31 pixels";
   if (size_t(dev.max_smem_optin) < 232448) return "needs 227 KB of shared memory per CTA";
   return nullptr;
 }
@@ -777,7 +782,7 @@ int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo&
   static const int issuers_env = env_int("XMM_RDB_MULTI_ISSUE", 1);
   a.multi_issue = issuers_env ? 1 : 0;
   static const int backoff_env = env_int("XMM_RDB_BACKOFF_NS", 0);
-  static const int prefetch_env = env_int("XMM_RDB_PREFETCH_ROWS", 0);
+  static const int prefetch_env = env_int("XMM_RDB_PREFETCH_ROWS", 3);  // measured: 3.13 -> 3.06 ms per block at batch 64
   a.backoff_ns = backoff_env;
   a.prefetch_rows = prefetch_env;
   constexpr int kBarBytes = 1024;
@@ -838,9 +843,15 @@ int launch_rdb_block(const xmm_conv3x3_params* L, bool skip_dead, const DeviceIn
   return launch_rdb<4, 2>(L + 3, store_b, dev, stream);
 }
 
+namespace {
+thread_local int g_last_chain_launches = 0;
+}
+extern "C" int xmm_last_chain_launches(void) { return g_last_chain_launches; }
+
 extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlayers, int mode_flags, void* workspace,
                                       size_t workspace_bytes, void* stream) {
   XMM_REQUIRE(layers != nullptr && nlayers >= 1, "conv3x3_chain: no layers");
+  g_last_chain_launches = 0;
   const int mode = mode_flags & 0xff;
   const bool skip_dead = (mode_flags & XMM_CHAIN_SKIP_DEAD_STORES) != 0;
   XMM_REQUIRE(mode >= 0 && mode <= 3 && (mode_flags & ~(0xff | XMM_CHAIN_SKIP_DEAD_STORES)) == 0,
@@ -857,7 +868,10 @@ extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlay
   static const int rdb_env = env_int("XMM_RDB", 1);
   if (mode == 3 || (mode == 0 && rdb_env)) {
     const char* why_not = rdb_blocker(layers, nlayers, dev);
-    if (why_not == nullptr) return launch_rdb_block(layers, skip_dead, dev, s);
+    if (why_not == nullptr) {
+      g_last_chain_launches = 2;
+      return launch_rdb_block(layers, skip_dead, dev, s);
+    }
     if (mode == 3) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3_chain: cannot fuse the dense block (%s)", why_not);
   }
   const char* why = chain_blocker(layers, nlayers);
@@ -867,12 +881,14 @@ extern "C" int xmm_conv3x3_chain_bf16(const xmm_conv3x3_params* layers, int nlay
     const size_t need = xmm_conv3x3_chain_workspace_bytes(nlayers, layers[0].batch, layers[0].height);
     XMM_REQUIRE(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 3) == 0,
                 "conv3x3_chain: workspace of %zu bytes needed (got %zu)", need, workspace_bytes);
+    g_last_chain_launches = 1;
     return launch_chain(layers, nlayers, dev, static_cast<int*>(workspace), s);
   }
   for (int l = 0; l < nlayers; ++l) {
     rc = xmm_conv3x3_bf16(&layers[l], stream);
     if (rc != XMM_OK) return rc;
   }
+  g_last_chain_launches = nlayers;
   return XMM_OK;
 }
 

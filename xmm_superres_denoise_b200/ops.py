@@ -16,6 +16,7 @@ from ._lib import (Conv3x3Params, ConvFirstParams, ConvLastParams, EdgeWgradPara
                    WgradParams, WgradRole)
 
 
+LAST_CHAIN_LAUNCHES = 0
 LAUNCHES = 0  # kernels launched through this module since the caller last reset it (bench.py's gpu_launches)
 
 
@@ -132,7 +133,9 @@ def conv3x3_chain(layers, mode: int = CHAIN_AUTO) -> None:
         ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
         _chain_ws[dev] = ws
     _lib.check(lib.xmm_conv3x3_chain_bf16(arr, n, int(mode), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
-    _count(1 if (mode & 0xff) == CHAIN_PIPELINED else n)  # (the fused form is 2 launches; counted as its n layers)
+    global LAST_CHAIN_LAUNCHES
+    LAST_CHAIN_LAUNCHES = int(lib.xmm_last_chain_launches())  # 2 fused, 1 pipelined, n layer by layer
+    _count(LAST_CHAIN_LAUNCHES)
 
 
 def conv_first(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
