@@ -170,7 +170,7 @@ def main():
     for nl, g, batch, band_h, width, grid in cases:
         ntx = tiles_x(width, nl)
         grid = min(grid, batch * ntx * band_h)
-        stages = 5 if nl == 3 else 4
+        stages = 5 if nl == 3 else 5
         for cta in sorted(set([0, 1, grid // 2, grid - 1])):
             pieces = cta_pieces(cta, grid, batch, band_h, width, nl)
             ok, info = simulate(nl, g, pieces, stages)

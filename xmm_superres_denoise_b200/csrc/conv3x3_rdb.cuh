@@ -253,6 +253,17 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[31])
       : "memory");
 }
+// 32-byte global accesses (LDG.256 / STG.256 on sm_100): a lane's 64-byte pixel row in two instructions
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory carve-up, identical in every thread.
@@ -278,7 +289,7 @@ template <int G, int NL, int L>
 __device__ __forceinline__ void rdb_issuer(const RdbArgs& args, const RdbCtx& c, const RdbSched<NL>& sched) {
   constexpr int NM = NL - 1;
   constexpr int e = NL - 1 - L;
-  constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};
+  constexpr int ring[2] = {NL == 3 ? 5 : 2, 3};
   rdb_wait(c.w_bar, 0, 7, L, 0);
   ptx::tc_fence_after();
   const uint64_t bdesc0 = ptx::umma_smem_desc(ptx::smem_u32(c.w_s), 16, 512, ptx::UMMA_SW64);
@@ -354,7 +365,7 @@ __device__ __forceinline__ void rdb_issuer(const RdbArgs& args, const RdbCtx& c,
 template <int G, int NL, int L>
 __device__ __forceinline__ void rdb_epilogue(const RdbArgs& args, const RdbCtx& c, const RdbSched<NL>& sched, int q, int lane) {
   constexpr int e = NL - 1 - L;
-  constexpr int ring[2] = {NL == 3 ? 5 : 3, 3};
+  constexpr int ring[2] = {NL == 3 ? 5 : 2, 3};
   constexpr bool last = L == NL - 1;
   const int pos = q * 32 + lane + 1;  // pixel position of this lane in a row tile
   const int band = pos >= kRdbBoxPx ? 1 : 0;
@@ -388,14 +399,14 @@ __device__ __forceinline__ void rdb_epilogue(const RdbArgs& args, const RdbCtx& 
       // residuals of the last layer: requested before the accumulator is waited for
       uint4 res1[4], res2[4];
       if (has_r1 && owned) {
-        const uint4* p = reinterpret_cast<const uint4*>(args.r1 + pix * args.r1_ctot + args.r1_coff);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) res1[k] = __ldg(p + k);
+        const __nv_bfloat16* p = args.r1 + pix * args.r1_ctot + args.r1_coff;
+        ld_global_nc_256(p, res1[0], res1[1]);
+        ld_global_nc_256(p + 16, res1[2], res1[3]);
       }
       if (has_r2 && owned) {
-        const uint4* p = reinterpret_cast<const uint4*>(args.r2 + pix * args.r2_ctot + args.r2_coff);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) res2[k] = __ldg(p + k);
+        const __nv_bfloat16* p = args.r2 + pix * args.r2_ctot + args.r2_coff;
+        ld_global_nc_256(p, res2[0], res2[1]);
+        ld_global_nc_256(p + 16, res2[2], res2[3]);
       }
       if (XMM_RDB_PROFILE)
         rdb_wait_p(&c.tfull[L], n & 1u, 5, L, int(n), prof, pw[0]);
@@ -482,6 +493,11 @@ __device__ __forceinline__ void rdb_epilogue(const RdbArgs& args, const RdbCtx& 
         ph[1] += t - tph;
         tph = t;
       }
+      if (args.layer[L].store && owned) {  // (before the map write: the stores drain while the fence below waits)
+        __nv_bfloat16* gp = args.layer[L].out + pix * args.layer[L].out_ctot + args.layer[L].out_coff;
+        st_global_256(gp, o[0], o[1]);
+        st_global_256(gp + 16, o[2], o[3]);
+      }
       if (!last) {
         // the next layers' A operand: row j of map L, swizzled as a TMA load would have written it; zeros outside
         // the image (padding) and on the junk lanes
@@ -501,11 +517,6 @@ __device__ __forceinline__ void rdb_epilogue(const RdbArgs& args, const RdbCtx& 
           ph[2] += t - tph;
           tph = t;
         }
-      }
-      if (args.layer[L].store && owned) {
-        uint4* gp = reinterpret_cast<uint4*>(args.layer[L].out + pix * args.layer[L].out_ctot + args.layer[L].out_coff);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) gp[k] = o[k];
       }
       if (XMM_RDB_PROFILE) {
         const long long t = clock64();

@@ -788,7 +788,7 @@ int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo&
   constexpr int kBarBytes = 1024;
   const long long room = (long long)dev.max_smem_optin - 1024 - kBarBytes - (long long)a.w_total;
   int tiles = int(room / kRdbTileBytes);
-  a.ring0 = NL == 3 ? 5 : 3;
+  a.ring0 = NL == 3 ? 5 : 2;  // (two fused layers: x4 is read one row behind its producer -- two tiles, one more TMA stage)
   a.ring1 = NL == 3 ? 3 : 0;
   a.stages = tiles - a.ring0 - a.ring1;
   if (a.stages > kRdbMaxStages) a.stages = kRdbMaxStages;
