@@ -361,6 +361,9 @@ def main() -> None:
         import torch.distributed as dist  # noqa: PLC0415
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduce is 6.7 MB (latency-bound): a handful of CTAs carry it; more only displace the
+        # persistent conv grids it overlaps with (TrainStep leaves XMM_COMM_SM_RESERVE SMs free meanwhile)
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
 
     from xmm_superres_denoise_b200 import _lib, ops
@@ -490,7 +493,7 @@ def main() -> None:
         del model, x_dev, counts_dev
         torch.cuda.empty_cache()
         short = argparse.Namespace(**vars(args))
-        short.steps, short.warmup, short.batch = min(args.steps, 5), 3, 0
+        short.steps, short.warmup, short.batch = min(args.steps, 20), 3, 0
         for kind in ("dn", "sr"):
             r = bench_train(short, kind, dev, dist, rank, world, local_rank, headline=False)
             if rank == 0:

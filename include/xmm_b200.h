@@ -39,6 +39,11 @@ const char* xmm_last_error(void);
 int xmm_version(void);
 /* 0 iff the current device is compute capability 10.x (sm_100a image present). */
 int xmm_check_device(void);
+/* Persistent kernels launch on (SM count - sms) CTAs from now on; returns the previous value.  Used by the data-parallel
+ * training step (training.TrainStep, replacing Lightning's DDP of train.py:148-155) while NCCL's all-reduce kernels
+ * share the GPU with the backward pass: a 148-CTA grid whose work was divided for 148 resident CTAs would otherwise
+ * run its last CTAs as a second wave.  0 restores the full GPU. */
+int xmm_set_sm_reserve(int sms);
 
 /* Weight repacking ------------------------------------------------------------------- */
 /* One source tensor contributing a run of K (input-channel) positions of a packed layer.

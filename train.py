@@ -1,15 +1,21 @@
 #!/usr/bin/env python
 """Training entry point (reference: xmm_superres_denoise/train.py:19-165 ``python train.py fit run.toml``).
 
-The reference builds DatasetCfg / ModelCfg / LossCfg / TrainerCfg from a TOML run file and hands a LightningModule to
-``lightning.Trainer``.  This script keeps the TOML keys that concern the RRDB path ([model], [model.model],
-[model.optimizer], [loss], [dataset] scaling / maxima / resolutions, [trainer] epochs / devices) and runs:
+The reference builds DatasetCfg / ModelCfg / LossCfg / TrainerCfg from a TOML run file plus ``res/configs/models.toml``
+and ``res/configs/loss_functions.toml`` and hands a LightningModule to ``lightning.Trainer``.  Lightning, astropy and
+the pydantic schemas are outside the accelerated path (out of scope) and not installed here, so
+this script is the plain-torch loop of ``xmm_superres_denoise_b200.training.TrainStep`` -- engine-direct
+forward/backward, NCCL all-reduce overlapped with backward, fused Adam -- on seeded Poisson count images of the
+reference shape (``--synthetic``; FITS directories need the reference's XmmDataModule).  There is no ``test``
+routine and no Lightning branch.  What it keeps of the reference's configuration, under the reference's key names:
 
-* with ``lightning`` installed: ``Trainer.fit(Model(...), datamodule)`` exactly like the reference (the datamodule is
-  the reference's own -- FITS decoding is outside the accelerated path);
-* without it (this image): the plain-torch loop of ``xmm_superres_denoise_b200.training.TrainStep`` -- engine-direct
-  forward/backward, NCCL all-reduce overlapped with backward, fused Adam -- on FITS directories fed through
-  ``data.CountsFeed`` or, with ``--synthetic``, on seeded Poisson count images of the reference shape.
+* the run file's [model] name / memory_efficient / batch_size, [dataset] scaling, lr / hr ``res``, ``exps`` / ``exp`` and
+  ``clamp_max`` (train.py:66-67: the normalisation maxima; ``max`` is accepted as an alias), [trainer] epochs;
+* ``res/configs/models.toml`` (train.py:35-36) when present in the working directory: the table named by
+  [model].name supplies in/out channels, filters, residual_blocks, learning_rate and betas;
+* ``res/configs/loss_functions.toml`` (train.py:45-53) when present: the [loss] percentages and, with
+  ``use_scaling = true``, the [scaling.<dataset scaling>] table as ``sc_dict`` of ``create_loss``.  Without the file the
+  [loss] table of the run file is used, unscaled (the scaling constants live in that file only).
 
     python train.py fit run.toml [--synthetic] [--steps N]
     python -m torch.distributed.run --nproc-per-node 8 train.py fit run.toml --synthetic
@@ -56,6 +62,25 @@ def load_run_config(path):
     if path:
         with open(path, "rb") as f:
             cfg = _merge(DEFAULTS, tomllib.load(f))
+    for side in ("lr", "hr"):  # train.py:66-67 reads dataset.<side>.clamp_max
+        if "clamp_max" in cfg["dataset"][side]:
+            cfg["dataset"][side]["max"] = cfg["dataset"][side]["clamp_max"]
+    models_toml = os.path.join("res", "configs", "models.toml")  # train.py:35-42
+    if os.path.exists(models_toml):
+        with open(models_toml, "rb") as f:
+            table = tomllib.load(f).get(cfg["model"]["name"])
+        if table is not None:
+            table = dict(table)
+            cfg["model"]["optimizer"] = {"learning_rate": table.pop("learning_rate"), "betas": table.pop("betas")}
+            cfg["model"]["model"] = _merge(cfg["model"]["model"], table)
+    cfg["sc_dict"] = None
+    loss_toml = os.path.join("res", "configs", "loss_functions.toml")  # train.py:45-53
+    if os.path.exists(loss_toml):
+        with open(loss_toml, "rb") as f:
+            lc = tomllib.load(f)
+        cfg["loss"] = dict(lc["loss"])
+        if cfg["loss"].get("use_scaling"):
+            cfg["sc_dict"] = lc["scaling"][cfg["dataset"]["scaling"]]
     return cfg
 
 
@@ -96,6 +121,7 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")  # a 6.7 MB all-reduce needs no more; see TrainStep.sm_reserve
         dist.init_process_group("nccl")
     if not a.synthetic:
         raise SystemExit("FITS datasets are read by the reference's XmmDataModule (astropy); run with --synthetic here, "
@@ -104,7 +130,7 @@ def main() -> None:
     d = cfg["dataset"]
     kind = "sr" if d["hr"]["res"] > d["lr"]["res"] else "dn"
     mcfg.name = "esr_gen" if kind == "sr" else "rrdb_denoise"
-    loss = create_loss(None, {k: float(v) for k, v in cfg["loss"].items() if k != "use_scaling"}).to(dev)
+    loss = create_loss(cfg["sc_dict"], {k: float(v) for k, v in cfg["loss"].items() if k != "use_scaling"}).to(dev)
     model = Model(mcfg, (d["lr"]["res"],) * 2, (d["hr"]["res"],) * 2, loss)
     model.configure_model()
     model = model.to(dev).train()

@@ -134,6 +134,7 @@ SIGNATURES = {
     "xmm_last_error": (c_char_p, []),
     "xmm_version": (c_int, []),
     "xmm_check_device": (c_int, []),
+    "xmm_set_sm_reserve": (c_int, [c_int]),
     "xmm_pack_blob_bytes": (c_size_t, [c_int, c_int, c_int]),
     "xmm_pack_weights": (c_int, [c_void_p, c_int, c_void_p]),
     "xmm_conv3x3_bf16": (c_int, [POINTER(Conv3x3Params), c_void_p]),

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <atomic>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -51,6 +52,13 @@ struct DeviceInfo {
 };
 
 // Per-device info, cached (the GPU under one process never changes: one process per GPU).
+// SMs the persistent kernels leave free (xmm_set_sm_reserve): while a collective's kernels share the GPU with a
+// 148-CTA persistent grid whose work was divided for 148 resident CTAs, the CTAs that do not fit run as a second wave.
+inline std::atomic<int>& sm_reserve() {
+  static std::atomic<int> v{0};
+  return v;
+}
+
 inline int device_info(DeviceInfo* out) {
   static std::mutex mu;
   static DeviceInfo cache[64];
@@ -69,6 +77,8 @@ inline int device_info(DeviceInfo* out) {
     d.max_smem_optin = int(p.sharedMemPerBlockOptin);
   }
   *out = d;
+  const int reserve = sm_reserve().load(std::memory_order_relaxed);
+  if (reserve > 0 && out->sm_count - reserve >= 8) out->sm_count -= reserve;
   return XMM_OK;
 }
 

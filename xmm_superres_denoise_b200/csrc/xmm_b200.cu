@@ -843,6 +843,11 @@ int launch_rdb_block(const xmm_conv3x3_params* L, bool skip_dead, const DeviceIn
   return launch_rdb<4, 2>(L + 3, store_b, dev, stream);
 }
 
+extern "C" int xmm_set_sm_reserve(int sms) {
+  if (sms < 0) sms = 0;
+  return sm_reserve().exchange(sms);
+}
+
 namespace {
 thread_local int g_last_chain_launches = 0;
 }

@@ -127,6 +127,11 @@ class TrainStep:
         self.opt = FusedAdam(self.flat, lr, betas, on_update=self.engine.arena.invalidate)
         self.overlap = overlap_allreduce and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.overlap else None
+        # SMs left to NCCL's kernels while the overlapped all-reduce chunks are in flight (XMM_COMM_SM_RESERVE, default
+        # 4 = NCCL_MAX_CTAS as set by train.py / bench.py): the conv / weight-gradient kernels are persistent grids of one
+        # CTA per SM whose work is divided for that many CTAs, so the CTAs a collective displaces would run as a
+        # second wave.  The reserve is set when the first chunk is released and dropped after the last wait.
+        self.sm_reserve = int(os.environ.get("XMM_COMM_SM_RESERVE", "4")) if self.overlap else 0
         self._works: List = []
         self._ones = torch.ones(1, dtype=torch.float32, device=self.flat.device)
         # chunk boundaries of the flat buffer: one chunk per RRDB (parameters are registered in module order)
@@ -154,6 +159,8 @@ class TrainStep:
         if self.world == 1 or hi <= lo:
             return
         if self.overlap:
+            if self.sm_reserve > 0 and not self._works:
+                _lib.load().xmm_set_sm_reserve(self.sm_reserve)
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self._works.append(dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
@@ -181,6 +188,8 @@ class TrainStep:
         self._allreduce_range(flat_grad, 0, done[0])
         for w in self._works:
             w.wait()
+        if self._works and self.sm_reserve > 0:
+            _lib.load().xmm_set_sm_reserve(0)
         self._works.clear()
         return st, flat_grad
 
