@@ -110,3 +110,27 @@ def test_state_update_compute_reset_and_errors(dev):
         create_loss(None, {"l1": 1.0})(preds=p, target=t)
     with pytest.raises(AssertionError):
         create_loss(None, {"l1": 0.0})
+
+
+def test_against_torchmetrics_when_the_box_has_it(dev):
+    """The reference's loss terms ARE torchmetrics objects (utils/loss_functions.py:3-9, metrics/metrics.py:9-39).
+    torchmetrics is in neither this image nor the authoring container, so the oracle for these terms is pinned to an
+    independent float64 scipy implementation instead (tests/test_oracle_loss.py).  Wherever the package does exist,
+    this test compares the CUDA loss directly with torchmetrics; otherwise the skip reason records its absence."""
+    try:
+        import torchmetrics  # noqa: F401
+        from torchmetrics import MeanAbsoluteError
+        from torchmetrics.image import (MultiScaleStructuralSimilarityIndexMeasure, PeakSignalNoiseRatio,
+                                        StructuralSimilarityIndexMeasure)
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"torchmetrics absent on this box ({type(e).__name__}: {e}); the loss oracle stays pinned to scipy float64")
+    from xmm_superres_denoise_b200.utils.loss_functions import create_loss
+
+    p, t = _pair(2, 416, 416, 3)
+    pd, td = p.to(dev), t.to(dev)
+    for name, metric in (("l1", MeanAbsoluteError()), ("psnr", PeakSignalNoiseRatio()),
+                         ("ssim", StructuralSimilarityIndexMeasure(kernel_size=13, sigma=2.5, k2=0.05)),
+                         ("ms_ssim", MultiScaleStructuralSimilarityIndexMeasure(kernel_size=13, sigma=2.5, k2=0.05))):
+        want = float(metric(p, t))
+        got = float(create_loss(None, {name: 1.0}).to(dev)(preds=pd, target=td))
+        assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (name, got, want)

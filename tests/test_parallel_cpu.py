@@ -53,7 +53,16 @@ def _worker(rank, world, port, out):
         lo, hi = shard_range(5, rank, world)
         gathered = [None] * world
         dist.all_gather_object(gathered, (lo, hi))
-        out.put((rank, bool(ok), gathered))
+        # validation-state reduction (CompositeLoss / metric collection): the accumulated sums are summed over the
+        # ranks and PSNR's running target range is the global min / max, as torchmetrics' dist_reduce_fx does --
+        # not a mean of per-rank values
+        from xmm_superres_denoise_b200.loss import CompositeLoss
+
+        loss = CompositeLoss({"l1": 1.0, "psnr": 1.0})
+        loss._acc.update({"abs": torch.tensor(2.0 + rank), "sq": torch.tensor(0.5 * (rank + 1)), "n": 10 * (rank + 1), "b": 1,
+                          "min_t": torch.tensor(0.0), "max_t": torch.tensor(0.5 + 0.25 * rank)})
+        total = float(loss.compute())
+        out.put((rank, bool(ok), gathered, total))
     finally:
         dist.destroy_process_group()
 
@@ -71,6 +80,11 @@ def test_gloo_world2_allreduce_and_sharding():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ok, gathered in results:
+    import math
+
+    l1 = (2.0 + 3.0) / 30.0                                    # sum |e| over both ranks / all pixels
+    psnr = 10.0 * math.log10(0.75 ** 2 / ((0.5 + 1.0) / 30.0))  # global range (max over ranks), global MSE
+    for rank, ok, gathered, total in results:
         assert ok, f"rank {rank}: all-reduce mean mismatch"
         assert gathered == [(0, 3), (3, 5)]
+        assert abs(total - (l1 + psnr)) < 1e-4, (rank, total, l1 + psnr)

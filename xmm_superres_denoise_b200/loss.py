@@ -288,8 +288,33 @@ class CompositeLoss(nn.Module):
             if name in st:
                 a[name] = a[name] + st[name].img_val.detach().sum()
 
-    def compute(self) -> torch.Tensor:
+    def _synced_state(self) -> dict:
+        """The accumulated state summed over the ranks of the default process group (torchmetrics declares these
+        states with dist_reduce_fx="sum" / min / max and reduces them in compute(); Lightning's sync_dist relies on
+        it): a mean of per-rank values is not the global metric, least of all for PSNR's running data range."""
         a = self._acc
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) or a["n"] == 0:
+            return a
+        dev = next((v.device for v in a.values() if isinstance(v, torch.Tensor)), None)
+        if dev is None:
+            return a
+        keys = ["abs", "poisson", "sq", "ssim", "ms_ssim", "n", "b"]
+        vec = torch.stack([torch.as_tensor(a[k], dtype=torch.float64, device=dev).reshape(()) for k in keys])
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        out = dict(a)
+        for k, v in zip(keys, vec):
+            out[k] = int(round(float(v))) if k in ("n", "b") else v.to(torch.float32)
+        if a["min_t"] is not None:
+            lo, hi = a["min_t"].clone(), a["max_t"].clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            out["min_t"], out["max_t"] = lo, hi
+        return out
+
+    def compute(self) -> torch.Tensor:
+        a = self._synced_state()
         if a["n"] == 0:
             raise RuntimeError("compute() called before update()")
         terms = {}

@@ -33,7 +33,7 @@ class MetricSet(CompositeLoss):
         super().__init__({"l1": 1.0, "poisson": 1.0, "psnr": 1.0, "ssim": 1.0, "ms_ssim": 1.0})
 
     def compute_all(self) -> Dict[str, torch.Tensor]:
-        a = self._acc
+        a = self._synced_state()  # summed over ranks (torchmetrics: dist_reduce_fx on every state)
         if a["n"] == 0:
             raise RuntimeError("compute() called before update()")
         dr = a["max_t"] - a["min_t"]
