@@ -324,27 +324,41 @@ __device__ __forceinline__ void rdb_issuer(const RdbArgs& args, const RdbCtx& c,
       ptx::tc_fence_after();
       if (r <= r_last) {
         const uint32_t d = c.tmem_base + uint32_t(L * kRdbSlotCols + rdb_phi(r - 1) * 32);
+        auto global_chunks = [&]() {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int k = int(fills & 7u);
-          rdb_wait_p(&c.lfull[L * 8 + k], (fills >> 3) & 1u, 3, L, k, prof, pw[1]);
-          const int stage = c.lstage[L * 8 + k];
-          ++fills;
-          ptx::tc_fence_after();
-          issue6(d, a_lo0 + uint32_t(stage) * kTile16, b_l + uint32_t(g * 9) * kTap16);
-          ptx::umma_commit(&c.empty[stage]);
-        }
-#pragma unroll
-        for (int m = 0; m < NM; ++m)
-          if (m < L) {
-            const int sq = seq[m] + (r - (pc.ra - (NL - 1 - m)));
-            const int slot = sq % ring[m];
-            rdb_wait_p(&c.mfull[m * 8 + slot], uint32_t(sq / ring[m]) & 1u, 4, L * 10 + m, sq, prof, pw[2]);
+          for (int g = 0; g < G; ++g) {
+            const int k = int(fills & 7u);
+            rdb_wait_p(&c.lfull[L * 8 + k], (fills >> 3) & 1u, 3, L, k, prof, pw[1]);
+            const int stage = c.lstage[L * 8 + k];
+            ++fills;
             ptx::tc_fence_after();
-            issue6(d, a_map0[m] + uint32_t(slot) * kTile16, b_l + uint32_t((G + m) * 9) * kTap16);
-            // the last layer that reads this row gives the tile back: layer L+1 reads rows [ra-e, rb+e-1]
-            if (L == NL - 1 || r < pc.ra - e || r > pc.rb + e - 1) ptx::umma_commit(&c.mempty[m * 8 + slot]);
+            issue6(d, a_lo0 + uint32_t(stage) * kTile16, b_l + uint32_t(g * 9) * kTap16);
+            ptx::umma_commit(&c.empty[stage]);
           }
+        };
+        auto map_chunks = [&]() {
+#pragma unroll
+          for (int m = 0; m < NM; ++m)
+            if (m < L) {
+              const int sq = seq[m] + (r - (pc.ra - (NL - 1 - m)));
+              const int slot = sq % ring[m];
+              rdb_wait_p(&c.mfull[m * 8 + slot], uint32_t(sq / ring[m]) & 1u, 4, L * 10 + m, sq, prof, pw[2]);
+              ptx::tc_fence_after();
+              issue6(d, a_map0[m] + uint32_t(slot) * kTile16, b_l + uint32_t((G + m) * 9) * kTap16);
+              // the last layer that reads this row gives the tile back: layer L+1 reads rows [ra-e, rb+e-1]
+              if (L == NL - 1 || r < pc.ra - e || r > pc.rb + e - 1) ptx::umma_commit(&c.mempty[m * 8 + slot]);
+            }
+        };
+        // Two fused layers: the in-CTA map first -- x4 was written a round ago, while the four global chunks of this
+        // step may still be landing in the few stages the weights leave room for.  (The order of the K chunks only
+        // changes the order of the fp32 sums.)
+        if (NL == 2) {
+          map_chunks();
+          global_chunks();
+        } else {
+          global_chunks();
+          map_chunks();
+        }
       }
       ptx::umma_commit(&c.tfull[L]);  // row r-1 is complete
     }
