@@ -127,11 +127,12 @@ class TrainStep:
         self.opt = FusedAdam(self.flat, lr, betas, on_update=self.engine.arena.invalidate)
         self.overlap = overlap_allreduce and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.overlap else None
-        # SMs left to NCCL's kernels while the overlapped all-reduce chunks are in flight (XMM_COMM_SM_RESERVE, default
-        # 4 = NCCL_MAX_CTAS as set by train.py / bench.py): the conv / weight-gradient kernels are persistent grids of one
-        # CTA per SM whose work is divided for that many CTAs, so the CTAs a collective displaces would run as a
-        # second wave.  The reserve is set when the first chunk is released and dropped after the last wait.
-        self.sm_reserve = int(os.environ.get("XMM_COMM_SM_RESERVE", "4")) if self.overlap else 0
+        # SMs left to NCCL's kernels while the overlapped all-reduce chunks are in flight (XMM_COMM_SM_RESERVE; 0 = off,
+        # the default): the conv / weight-gradient kernels are persistent grids of one CTA per SM whose work is divided
+        # for that many CTAs, so CTAs a collective displaces would run as a second wave.  Measured on 8 x B200
+        # (profiles/r02_scale_1_vs_8gpu_comm_knobs.log): reserve 0 / 4 / 8 and NCCL_MAX_CTAS 4 / 8 / 32 all give
+        # 2622..2635 img/s (SR training) -- the 4 % the step loses at 8 GPUs is not SM contention -- so it stays off.
+        self.sm_reserve = int(os.environ.get("XMM_COMM_SM_RESERVE", "0")) if self.overlap else 0
         self._works: List = []
         self._ones = torch.ones(1, dtype=torch.float32, device=self.flat.device)
         # chunk boundaries of the flat buffer: one chunk per RRDB (parameters are registered in module order)
