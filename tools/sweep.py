@@ -28,7 +28,7 @@ def flops_per_image(kind: str, nf: int, nb: int, pixels: int = 416 * 416) -> flo
 
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_sweep.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_sweep.json"))
     ap.add_argument("--kind", default="dn", choices=["dn", "sr"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--blocks", default="8,16,23")
@@ -84,9 +84,11 @@ def main() -> None:
             if not a.no_cpu:
                 torch.set_num_threads(os.cpu_count() or 1)
                 with torch.no_grad():
-                    t0 = time.perf_counter()
-                    O.model_forward(x8[:1], sd, a.kind, 1)
-                    dt = time.perf_counter() - t0
+                    O.model_forward(x8[:1], sd, a.kind, 1)  # warm-up (oneDNN primitive creation, page faults): the round-1
+                    t0 = time.perf_counter()                # rows timed this first call and were inconsistent
+                    for _ in range(2):
+                        O.model_forward(x8[:2], sd, a.kind, 1)
+                    dt = (time.perf_counter() - t0) / 4
                 cpu_rows.append({"filters": nf, "blocks": nb, "batch": 1, "images_per_s": 1.0 / dt, "s_per_image": dt,
                                  "cores": os.cpu_count(), "kind": "port (oracle, torch %s fp32)" % torch.__version__})
                 print(cpu_rows[-1], flush=True)
