@@ -85,6 +85,7 @@ def test_full_gradient_vector_vs_oracle(dev, kind):
     print(f"{kind}: full gradient rel-L2 = {r:.3e}")
     assert r < GRAD_REL
     per = {n: rel_l2(p.grad.cpu(), sdg[n].grad) for n, p in m.named_parameters() if sdg[n].grad.norm() > 0}
+    print(f"{kind}: worst tensors {sorted(((round(v, 5), n) for n, v in per.items()), reverse=True)[:3]}")
     bad = {n: v for n, v in per.items() if v > 5 * GRAD_REL}
     assert not bad, bad
 
@@ -148,9 +149,11 @@ def test_64_filter_gradients_vs_oracle(dev, kind):
           f"{max(per, key=per.get)} = {max(per.values()):.3e}")
     assert r_out < REL_L2_BF16
     assert r < GRAD_REL
-    # conv_first.weight (576 numbers) is x correlated with the SUM of two bf16-stored gradient maps that largely cancel
-    # at nb = 1 -- the same conditioning as dL/dx in test_gradients_match_reference_golden; held to 1e-1
-    bad = {n: v for n, v in per.items() if v > (1e-1 if n == "conv_first.weight" else 5 * GRAD_REL)}
+    # Every tensor within north_star's 1e-2 (measured worst: 6.2e-3 DN, 8.6e-3 SR) -- except conv_first.weight (576
+    # numbers): x correlated with the SUM of two bf16-stored gradient maps (through the RRDB chain + the trunk skip) that
+    # largely cancel at nb = 1; measured 5.8e-2 (DN) / 1.3e-2 (SR).  Forming the sum before rounding needs a third
+    # residual input in the data-gradient epilogue; at nb >= 2 the two maps no longer cancel.
+    bad = {n: v for n, v in per.items() if v > (6e-2 if n == "conv_first.weight" else GRAD_REL)}
     assert not bad, bad
 
 
