@@ -126,7 +126,29 @@ def simulate(nl, g, pieces, stages, verbose=False):
                     mfull[l][slot].arrive()
         return
 
-    agents = {"producer": producer()}
+    def layer_producer(l, s0, ns):
+        idx, phase, fills = 0, 0, 0
+        for (p, r, flush, n, seq) in layer_steps(pieces, nl, l):
+            if flush:
+                continue
+            for _ in range(g):
+                stage = s0 + idx
+                while not empty[stage].ready(phase ^ 1):
+                    yield ("empty", stage)
+                k = fills % 8
+                fills += 1
+                lstage[l][k] = stage
+                tma.append([3, lfull[l][k]])
+                idx += 1
+                if idx == ns:
+                    idx, phase = 0, phase ^ 1
+        return
+
+    if nl == 2:   # one producer and stage-ring slice per layer (conv3x3_rdb.cuh: rdb_layer_producer)
+        ns0 = (stages + 1) // 2
+        agents = {"producer0": layer_producer(0, 0, ns0), "producer1": layer_producer(1, ns0, stages - ns0)}
+    else:
+        agents = {"producer": producer()}
     for l in range(nl):
         agents[f"issuer{l}"] = issuer(l)
         agents[f"epi{l}"] = epilogue(l)

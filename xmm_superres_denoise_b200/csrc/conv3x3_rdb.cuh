@@ -81,6 +81,7 @@ struct RdbArgs {
   int r2_ctot, r2_coff;
   int backoff_ns;   // nanosleep between polls of the producer / epilogue waits (0: none)
   int prefetch_rows;  // the producer asks L2 for the global maps of the row this many steps ahead (0: off)
+  int split_producers;  // two fused layers: one TMA producer thread and stage-ring slice per layer
   int multi_issue;  // 1: one issuer thread per layer (warps 1..NL); 0: warp 1 issues every layer
   long long* prof;  // optional (XMM_RDB_PROF=1): 16 cycle counters per CTA, see launch_rdb
 };
@@ -556,6 +557,66 @@ __device__ __forceinline__ void rdb_epilogue(const RdbArgs& args, const RdbCtx& 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- TMA producer
+// (two fused layers) One producer thread PER LAYER, each with its own slice [s0, s0 + ns) of the stage ring: with the
+// 166 KB of weights of conv4 + conv5 only five stages fit, and one thread walking both layers' steps in one shared ring
+// could not keep them full (the issuer of conv4 waited 31 % of its time for chunks).  A layer's thread only follows
+// its own layer -- pieces in order, rows top to bottom -- and only waits for its own layer's MMAs.
+template <int G, int NL, int L>
+__device__ __forceinline__ void rdb_layer_producer(const CUtensorMap* tmap_in, const RdbArgs& args, const RdbCtx& c,
+                                                   const RdbSched<NL>& sched, int s0, int ns) {
+  constexpr int e = NL - 1 - L;
+  int idx = 0;
+  uint32_t phase = 0;
+  uint32_t fills = 0;
+  for (int pi = 0; pi < sched.npieces; ++pi) {
+    const RdbPiece pc = sched.get(pi);
+    for (int r = pc.ra - e - 1; r <= pc.rb + e; ++r) {
+      int row = r, band0 = 0;
+      if (r < 0) {
+        row = r + args.band_h;
+        band0 = -1;
+      } else if (r >= args.band_h) {
+        row = r - args.band_h;
+        band0 = 1;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int stage = s0 + idx;
+        rdb_wait_backoff(&c.empty[stage], phase ^ 1u, 1, L, stage, uint32_t(args.backoff_ns));
+        const int k = int(fills++ & 7u);
+        c.lstage[L * 8 + k] = stage;
+        uint64_t* fb = &c.lfull[L * 8 + k];
+        ptx::mbar_expect_tx(fb, kRdbTileData);
+        ptx::tma_load_5d(c.stage_s + size_t(stage) * kRdbTileBytes, tmap_in, fb, args.cin_off + 32 * g, pc.x0 - 1, row, band0, pc.b);
+        if (++idx == ns) {
+          idx = 0;
+          phase ^= 1u;
+        }
+      }
+      if (L == 0 && args.prefetch_rows > 0) {  // the first layer's rows come from HBM: ask L2 for them ahead of time
+        const int rp = r + args.prefetch_rows;
+        if (rp <= pc.rb + e) {
+          int prow = rp, pband = 0;
+          if (rp < 0) {
+            prow = rp + args.band_h;
+            pband = -1;
+          } else if (rp >= args.band_h) {
+            prow = rp - args.band_h;
+            pband = 1;
+          }
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+            asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                             reinterpret_cast<uint64_t>(tmap_in)),
+                         "r"(args.cin_off + 32 * g), "r"(pc.x0 - 1), "r"(prow), "r"(pband), "r"(pc.b)
+                         : "memory");
+        }
+      }
+    }
+  }
+}
+
 // G: feature maps read from global memory (x0 .. x_{G-1}); NL: fused layers.  Layer l (0-based) is conv_{G+l}: its K
 // chunks are the G global maps then the l maps produced in this CTA.
 // Warp roles (512 threads): warp 0 = TMA producer (the only role that follows the interleaved walk: it decides the
@@ -649,7 +710,14 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
   RdbSched<NL> sched;
   sched.init(args);
 
-  if (warp == 0) {
+  if (NL == 2 && args.split_producers && (warp == 0 || warp == 3)) {
+    // ------------------------------------------------------------ TMA producers, one per layer (warps 0 and 3)
+    if (ptx::elect_one()) {
+      const int ns0 = (args.stages + 1) / 2;  // conv4 (whose rows come from HBM) gets the larger half
+      if (warp == 0) rdb_layer_producer<G, NL, 0>(&tmap_in, args, c, sched, 0, ns0);
+      if (warp == 3) rdb_layer_producer<G, NL, 1>(&tmap_in, args, c, sched, ns0, args.stages - ns0);
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       int stage = 0;
@@ -706,7 +774,7 @@ conv3x3_rdb_kernel(const __grid_constant__ CUtensorMap tmap_in, const RdbArgs ar
       });
     }
   } else if (warp <= 3) {
-    if (warp - 1 < NL && ptx::elect_one()) {
+    if (warp - 1 < NL && ptx::elect_one()) {  // (warp 3 of a two-layer kernel: idle, or the second producer above)
       if (warp == 1) rdb_issuer<G, NL, 0>(args, c, sched);
       if (warp == 2) rdb_issuer<G, NL, 1>(args, c, sched);
       if constexpr (NL == 3) {

@@ -795,6 +795,10 @@ int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo&
   static const int stages_env = env_int("XMM_RDB_STAGES", 0);
   if (stages_env > 0 && stages_env < a.stages) a.stages = stages_env;
   if (a.stages < 3) return fail(XMM_ERR_UNSUPPORTED_SHAPE, "conv3x3 (fused dense block): %d pipeline stages fit", a.stages);
+  // measured (profiles/r02_rdb_v8_split_producers.log): 3.08 ms per block against 2.87 ms with one producer and one shared
+  // ring -- rings of 3 + 2 stages are less elastic than one of 5 -- so it is off
+  static const int split_env = env_int("XMM_RDB_SPLIT_PRODUCERS", 0);
+  a.split_producers = (NL == 2 && split_env && a.stages >= 4) ? 1 : 0;
   CUtensorMap tmap;
   int rc = cached_band_tmap(&tmap, L[0].in, a.batch, a.height, a.width, L[0].in_ctot, a.band_h, 2, 32, kRdbBoxPx, 2);
   if (rc != XMM_OK) return rc;
