@@ -82,7 +82,6 @@ struct RdbArgs {
   int backoff_ns;   // nanosleep between polls of the producer / epilogue waits (0: none)
   int prefetch_rows;  // the producer asks L2 for the global maps of the row this many steps ahead (0: off)
   int split_producers;  // two fused layers: one TMA producer thread and stage-ring slice per layer
-  int multi_issue;  // 1: one issuer thread per layer (warps 1..NL); 0: warp 1 issues every layer
   long long* prof;  // optional (XMM_RDB_PROF=1): 16 cycle counters per CTA, see launch_rdb
 };
 

@@ -779,8 +779,6 @@ int launch_rdb(const xmm_conv3x3_params* L, const bool* store, const DeviceInfo&
   a.s0 = pl.s0; a.s1 = pl.s1; a.s2 = pl.s2;
   a.r1 = static_cast<const __nv_bfloat16*>(pl.r1); a.r1_ctot = pl.r1_ctot; a.r1_coff = pl.r1_coff;
   a.r2 = static_cast<const __nv_bfloat16*>(pl.r2); a.r2_ctot = pl.r2_ctot; a.r2_coff = pl.r2_coff;
-  static const int issuers_env = env_int("XMM_RDB_MULTI_ISSUE", 1);
-  a.multi_issue = issuers_env ? 1 : 0;
   static const int backoff_env = env_int("XMM_RDB_BACKOFF_NS", 0);
   static const int prefetch_env = env_int("XMM_RDB_PREFETCH_ROWS", 3);  // measured: 3.13 -> 3.06 ms per block at batch 64
   a.backoff_ns = backoff_env;
