@@ -125,6 +125,13 @@ class TrainStep:
         self.engine = model._get_engine(train=True)
         self.engine.arena.invalidate()  # packed bf16 weight images follow the (possibly replaced) parameters
         self.opt = FusedAdam(self.flat, lr, betas, on_update=self.engine.arena.invalidate)
+        # XMM_COMM_MODE (experiments): "overlap" (default: chunks released per RRDB on a side stream), "serial" (one
+        # all-reduce after the backward pass), "none" (NO gradient exchange -- replicas diverge; only to measure what the
+        # collective costs next to the spread between the GPUs of a box)
+        self.comm_mode = os.environ.get("XMM_COMM_MODE", "overlap")
+        if self.comm_mode not in ("overlap", "serial", "none"):
+            raise ValueError(f"XMM_COMM_MODE={self.comm_mode!r}: expected overlap, serial or none")
+        overlap_allreduce = overlap_allreduce and self.comm_mode == "overlap"
         self.overlap = overlap_allreduce and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if self.overlap else None
         # SMs left to NCCL's kernels while the overlapped all-reduce chunks are in flight (XMM_COMM_SM_RESERVE; 0 = off,
@@ -157,7 +164,7 @@ class TrainStep:
     def _allreduce_range(self, flat_grad: torch.Tensor, lo: int, hi: int) -> None:
         import torch.distributed as dist
 
-        if self.world == 1 or hi <= lo:
+        if self.world == 1 or hi <= lo or self.comm_mode == "none":
             return
         if self.overlap:
             if self.sm_reserve > 0 and not self._works:
@@ -184,7 +191,7 @@ class TrainStep:
             done[0] = lo
 
         _, _ = eng.backward(bufs, eng.generation, lr_img, gout, need_x_grad=False,
-                            rrdb_done_hook=hook if self.world > 1 else None)
+                            rrdb_done_hook=hook if self.overlap else None)
         flat_grad = eng.last_flat_grad
         self._allreduce_range(flat_grad, 0, done[0])
         for w in self._works:
