@@ -20,9 +20,12 @@ Pinning status (see DESIGN.md "Oracle"):
   * MAE / PSNR / SSIM / MS-SSIM terms: the arithmetic lives in the third-party package
     ``torchmetrics`` (unpinned in the reference's Dockerfile:10; poetry.lock names 0.11.4
     but the imports need >= 1.0), which is neither vendored in the reference nor installed
-    here.  The reference holds no test or golden value at that boundary -> PARITY UNPINNED
-    for those terms; the restatement below follows torchmetrics >= 1.0
-    ``functional/image/ssim.py`` and is the definition used by this repository.
+    here, and the reference holds no test or golden value at that boundary.  The restatement
+    below follows torchmetrics >= 1.0 ``functional/image/ssim.py``.  It is pinned to an
+    INDEPENDENT implementation instead -- float64 SSIM / MS-SSIM / PSNR / MAE built on
+    ``scipy.ndimage`` Gaussian filtering (tests/test_oracle_loss.py, 416x416 and 832x832) -- and a
+    GPU test diffs the CUDA loss against torchmetrics itself wherever that package exists
+    (tests/test_gpu_loss.py).  Against torchmetrics proper these terms remain PARITY UNPINNED.
 """
 from __future__ import annotations
 
