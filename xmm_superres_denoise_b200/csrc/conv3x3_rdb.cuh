@@ -33,11 +33,15 @@
 // slots.  Every MMA accumulates: the epilogue zeroes a slot after draining it, and the issuer starts the step on
 // row r only after row r-2 has been drained (one barrier pair per layer, strictly alternating).
 //
-// Schedule.  One deterministic walk (rdb_walk) interleaves the layers -- L0 step, L1 step, L2 step, L0 step ... --
-// and is run identically by the TMA producer, the MMA issuer and the two epilogue groups.  Layer l may take its step
-// on row r when layer l-1 issued its step on row r+1 in an EARLIER round, so the rows it waits for were produced a
-// full round of MMAs ago and the tensor pipe does not drain while the epilogue works.  After the last row of a piece
-// a layer takes two flush steps (no MMAs) that complete and zero the two trailing partial rows.
+// Schedule and roles (512 threads).  One deterministic walk (rdb_walk) interleaves the layers -- L0 step, L1 step,
+// L2 step, L0 step ...; layer l takes its step on row r when layer l-1 took its step on row r+1 in an EARLIER round;
+// after the last row of a piece a layer takes two flush steps (no MMAs) that complete and re-initialise the two
+// trailing partial rows.  Only the TMA producer (warp 0) follows the walk: it decides the order in which rows are
+// loaded into the ONE stage ring all layers share (the stage id travels next to a per-layer "landed" barrier ring).
+// Layer l's MMA issuer (one thread of warp 1 + l) and its epilogue group (warps 4 + 4 l .. 7 + 4 l, one per TMEM lane
+// quarter) iterate their own layer only -- pieces in order, rows top to bottom -- and meet the other roles through
+// mbarriers.  Rule for every barrier here: its waiter observes EVERY phase (a parity wait two phases ahead passes at
+// once) -- hence per-layer barriers and per-layer roles; tools/rdb_protocol_sim.py models the whole protocol.
 #pragma once
 #include <cstdio>
 
