@@ -94,3 +94,37 @@ def test_model_wrapper_mirrors_reference_interface():
     bad = Model(types.SimpleNamespace(**{**cfg.__dict__, "name": "esr_gen"}), (416, 416), (1248, 1248), loss=None)
     with pytest.raises(ValueError):
         bad.configure_model()
+
+
+def test_train_py_reads_the_reference_config_files(tmp_path, monkeypatch):
+    """train.py (reference: xmm_superres_denoise/train.py:27-55,66-67): the model table of res/configs/models.toml named
+    by [model].name, the [loss] percentages + [scaling.<mode>] of res/configs/loss_functions.toml when use_scaling is
+    set, and dataset.<side>.clamp_max as the normalisation maxima."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("xmm_train_entry", os.path.join(root, "train.py"))
+    train = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(train)
+    cfgdir = tmp_path / "res" / "configs"
+    cfgdir.mkdir(parents=True)
+    (cfgdir / "models.toml").write_text(
+        '[esr_gen]\nin_channels = 1\nout_channels = 1\nfilters = 64\nresidual_blocks = 8\nlearning_rate = 2e-4\nbetas = [0.5, 0.9]\n')
+    (cfgdir / "loss_functions.toml").write_text(
+        '[loss]\nuse_scaling = true\nl1 = 0.25\npoisson = 0.0\npsnr = 0.0\nssim = 0.0\nms_ssim = 0.75\n'
+        '[scaling.sqrt]\nl1 = { scaling = 9.5, correction = -0.5 }\nms_ssim = { scaling = -3.0, correction = 2.6 }\n'
+        '[scaling.linear]\nl1 = { scaling = 27.0, correction = -0.57 }\n')
+    run = tmp_path / "run.toml"
+    run.write_text('[model]\nname = "esr_gen"\nbatch_size = 4\n[dataset]\nscaling = "sqrt"\n'
+                   '[dataset.lr]\nclamp_max = 0.002\nres = 416\nexps = [20]\n[dataset.hr]\nclamp_max = 0.0005\nres = 832\nexp = 50\n')
+    monkeypatch.chdir(tmp_path)
+    cfg = train.load_run_config(str(run))
+    assert cfg["model"]["model"]["filters"] == 64 and cfg["model"]["model"]["residual_blocks"] == 8
+    assert cfg["model"]["optimizer"] == {"learning_rate": 2e-4, "betas": [0.5, 0.9]}
+    assert cfg["dataset"]["lr"]["max"] == 0.002 and cfg["dataset"]["hr"]["max"] == 0.0005
+    assert cfg["loss"]["ms_ssim"] == 0.75 and cfg["sc_dict"]["l1"] == {"scaling": 9.5, "correction": -0.5}
+    # without the files: the run file's own tables, unscaled
+    monkeypatch.chdir(tmp_path / "res")
+    cfg = train.load_run_config(str(run))
+    assert cfg["sc_dict"] is None and cfg["model"]["model"]["filters"] == 32
